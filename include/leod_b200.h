@@ -1,0 +1,150 @@
+/*
+ * leod_b200 — C ABI of the B200-native LEOD hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer named *_dev* / documented as
+ * "device" must point to memory accessible from the current CUDA device; `stream` is a
+ * cudaStream_t passed as void*.  All functions return 0 on success and a negative value on
+ * failure; leod_last_error() then returns a thread-local, NUL-terminated description.  Nothing in
+ * this library aborts the process or falls back to the CPU.
+ *
+ * Each entry point cites the reference interface (paths relative to the LEOD tree) it replaces.
+ * Layouts: activations are channels-last ("NHWC", tokens x channels, row-major) in the handle's
+ * storage dtype (LEOD_F32 or LEOD_BF16); parameters and gradients are fp32.
+ */
+#ifndef LEOD_B200_H_
+#define LEOD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEOD_ABI_VERSION 1
+
+enum { LEOD_F32 = 0, LEOD_BF16 = 1, LEOD_U8 = 2 };
+
+const char *leod_last_error(void);
+int leod_abi_version(void);
+
+/* ------------------------------------------------------------------ recurrent backbone
+ * Replaces models/detection/recurrent_backbone/maxvit_rnn.py:23-115 (RNNDetector) and everything
+ * below it: maxvit.py:143-182, 185-270, 328-354, 85-118, 45-53 and models/layers/rnn.py:7-70. */
+typedef struct leod_backbone leod_backbone_t;
+
+typedef struct {
+  int32_t in_channels;  /* backbone.input_channels (20)                         */
+  int32_t embed_dim;    /* backbone.embed_dim 32/48/64; stage dims = x1,x2,x4,x8 */
+  int32_t dim_head;     /* stage.attention.dim_head                              */
+  int32_t part_h;       /* stage.attention.partition_size[0]                     */
+  int32_t part_w;       /* stage.attention.partition_size[1]                     */
+  int32_t mlp_ratio;    /* stage.attention.mlp_ratio (4)                         */
+  int32_t in_h;         /* padded input height, backbone.in_res_hw[0]            */
+  int32_t in_w;         /* padded input width,  backbone.in_res_hw[1]            */
+  int32_t dtype;        /* LEOD_F32 or LEOD_BF16: activation storage / GEMM operand type */
+  float ln_eps;         /* 1e-5                                                  */
+} leod_backbone_cfg;
+
+int leod_backbone_create(const leod_backbone_cfg *cfg, leod_backbone_t **out);
+/* Same, without any device allocation: only leod_backbone_param_info / _param_count / _save_bytes and
+ * _destroy are valid on the result (lets host code lay out parameters on a machine without a GPU). */
+int leod_backbone_layout_only(const leod_backbone_cfg *cfg, leod_backbone_t **out);
+void leod_backbone_destroy(leod_backbone_t *h);
+
+/* Flat fp32 parameter buffer layout.  Entry i has the reference's state_dict name (without the
+ * leading "backbone."), an element offset into the flat buffer and a shape (ndim <= 4).
+ * Returns the number of entries when i < 0. */
+int leod_backbone_param_info(const leod_backbone_t *h, int i, char *name, size_t name_cap, int64_t *offset,
+                             int32_t *ndim, int64_t shape[4]);
+int64_t leod_backbone_param_count(const leod_backbone_t *h); /* floats in the flat buffer */
+
+/* Bind the flat parameter / gradient buffers (device, fp32, leod_backbone_param_count floats). */
+int leod_backbone_bind(leod_backbone_t *h, float *params_dev, float *grads_dev);
+/* Re-derive the operand-typed, layout-prepared weight copies from the bound parameters.  Call after
+ * every parameter update (optimizer step, load_state_dict) and before the next forward. */
+int leod_backbone_prepare(leod_backbone_t *h, void *stream);
+
+int64_t leod_backbone_save_bytes(const leod_backbone_t *h, int B);
+
+/* One timestep, all four stages (maxvit_rnn.py:97-115).
+ *  x        : device, [B, in_channels, x_h, x_w] channel-first, dtype x_dtype (LEOD_F32/BF16/U8);
+ *             zero-padded on the fly to in_h x in_w (utils/padding.py:33-58, detection.py:132).
+ *  h_prev/c_prev : 4 device pointers (NHWC, storage dtype) or NULL entries = zero state (rnn.py:45-50)
+ *  h_out/c_out   : 4 device pointers (NHWC, storage dtype), written.  h_out[s] is feature s+1.
+ *  save     : device scratch of leod_backbone_save_bytes(B) bytes that keeps the activations needed
+ *             by leod_backbone_step_bwd, or NULL for inference. */
+int leod_backbone_step_fwd(leod_backbone_t *h, const void *x, int x_dtype, int x_h, int x_w, int B,
+                           const void *const h_prev[4], const void *const c_prev[4], void *const h_out[4],
+                           void *const c_out[4], void *save, void *stream);
+
+/* Backward of one timestep.  h_prev/c_prev/h_out/c_out: the tensors of the forward call.  dh_out/dc_out: gradients w.r.t. the step's outputs (NULL = zero);
+ * dh_prev/dc_prev: written (gradients w.r.t. the incoming state).  Parameter gradients are
+ * ACCUMULATED into the bound gradient buffer (and internal LayerScale scratch). */
+int leod_backbone_step_bwd(leod_backbone_t *h, const void *x, int x_dtype, int x_h, int x_w, int B,
+                           const void *const h_prev[4], const void *const c_prev[4], const void *const h_out[4],
+                           const void *const c_out[4], const void *save, const void *const dh_out[4], const void *const dc_out[4],
+                           void *const dh_prev[4], void *const dc_prev[4], void *stream);
+/* Fold the internal scratch into the bound gradient buffer; call once after the last step_bwd of a
+ * backward pass. */
+int leod_backbone_grads_finalize(leod_backbone_t *h, void *stream);
+/* Pre-size the internal workspace for batches up to B (call outside CUDA-graph capture). */
+int leod_backbone_reserve(leod_backbone_t *h, int B);
+/* 0 = SIMT GEMMs, 1 = tcgen05/TMA GEMMs (LEOD_BF16 handles only; their default). */
+int leod_backbone_set_gemm_impl(leod_backbone_t *h, int impl);
+
+/* ------------------------------------------------------------------ building blocks (exported for tests)
+ * C[M,N] = epilogue(A[M,K] * B[N,K]^T + bias).  A may be split in two sources along K
+ * (A for k < K1, A2 for k >= K1; pass A2 = NULL, K1 = K otherwise).  dtype: operand/output type.
+ * impl: 0 = SIMT fp32-accumulate kernel, 1 = tcgen05/TMA tensor-core kernel (LEOD_BF16 only).
+ * epi: 0 none, 1 C=gelu(v), aux=v   2 C = R + v   3 C = v * gelu'(aux). */
+int leod_gemm_nt(int impl, int dtype, const void *A, int lda, const void *A2, int lda2, int K1, const void *B, int ldb,
+                 void *C, int ldc, int M, int N, int K, const float *bias, int epi, const void *R, int ldr, void *aux,
+                 int ldaux, void *stream);
+/* dW[N,K] (fp32, ld ldw) += dY[M,N]^T * X[M,K];  dbias[N] += column sums of dY (if non-NULL). */
+int leod_gemm_tn(int impl, int dtype, const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias,
+                 int M, int N, int K, void *stream);
+
+/* Window / grid multi-head attention over an NHWC token matrix (maxvit.py:273-304, 343-354 minus the
+ * two Linear layers).  qkv [B*H*W, 3C] with per-head [q|k|v] column blocks; out [B*H*W, C]. */
+int leod_attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, int C, int dim_head, int ph, int pw,
+                       int window, void *stream);
+int leod_attention_bwd(int dtype, const void *qkv, const void *dout, void *dqkv, int B, int H, int W, int C, int dim_head,
+                       int ph, int pw, int window, void *stream);
+
+/* ------------------------------------------------------------------ detection post-processing
+ * Replaces models/detection/yolox/utils/boxes.py:32-86 (postprocess) including the
+ * torchvision.ops.batched_nms call at :73, batched over images with no host round trip.
+ *  pred  : device fp32 [B, A, 5+num_classes] = (cx, cy, w, h, obj, cls...) — NOT modified
+ *  out   : device fp32 [B, max_det, 7] rows (x1,y1,x2,y2,obj,cls_conf,cls_idx) in descending score order
+ *  count : device int32 [B] number of valid rows per image
+ * max_det <= A. */
+int leod_postprocess(const float *pred, int B, int A, int num_classes, float conf_thre, float nms_thre,
+                     int class_agnostic, float *out, int32_t *count, int max_det, void *stream);
+
+/* Replaces modules/utils/ssod.py:147-188 (pred2label) + :113-133 (filter_pred_boxes) on the packed
+ * output of leod_postprocess.  labels: device fp32 [B, max_det, 8] rows (t=0, x, y, w, h, cls,
+ * cls_conf, obj_conf), compacted per image; lab_count int32 [B].  obj_thresh/cls_thresh: host arrays
+ * of num_classes floats.  frame_h/frame_w <= 0 disables the box filter. */
+int leod_pred2label(const float *dets, const int32_t *count, int B, int max_det, int num_classes,
+                    const float *obj_thresh, const float *cls_thresh, int frame_h, int frame_w, float *labels,
+                    int32_t *lab_count, void *stream);
+
+/* ------------------------------------------------------------------ event binning
+ * Replaces data/utils/representations.py:78-123 (StackedHistogram.construct).
+ * x,y,p: device int32 [n]; t: device int64 [n] (sorted); out: device uint8 [2*bins, H, W].
+ * fastmode != 0 reproduces the uint8 wrap-around accumulation. */
+int leod_voxel_bin(const int32_t *x, const int32_t *y, const int32_t *p, const int64_t *t, int64_t n, int bins, int H,
+                   int W, int count_cutoff, int fastmode, uint8_t *out, void *stream);
+
+/* ------------------------------------------------------------------ optimizer / teacher update
+ * Fused AdamW (modules/detection.py:485-518; torch.optim.AdamW semantics) with gradient
+ * clip-by-value (train.py:236-237; clip_value <= 0 disables) over a flat fp32 buffer, `step` 1-based.
+ * If ema != NULL also applies modules/utils/ssod.py:429-438: ema = a*ema + (1-a)*p with the caller's a. */
+int leod_adamw_ema(float *p, const float *g, float *m, float *v, float *ema, int64_t n, int step, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float clip_value, float ema_alpha, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEOD_B200_H_ */

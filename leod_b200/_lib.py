@@ -1,0 +1,108 @@
+"""ctypes binding of libleod_b200.so (the C ABI in include/leod_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libleod_b200.so')
+
+LEOD_F32, LEOD_BF16, LEOD_U8 = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_RESID, EPI_GELU_BWD = 0, 1, 2, 3
+
+
+class BackboneCfg(Structure):
+    _fields_ = [('in_channels', c_int32), ('embed_dim', c_int32), ('dim_head', c_int32), ('part_h', c_int32),
+                ('part_w', c_int32), ('mlp_ratio', c_int32), ('in_h', c_int32), ('in_w', c_int32), ('dtype', c_int32),
+                ('ln_eps', c_float)]
+
+
+_VP4 = c_void_p * 4
+_lib = None
+
+
+def _declare(lib):
+    I, VP, F = c_int, c_void_p, c_float
+    sig = {
+        'leod_last_error': (c_char_p, []),
+        'leod_abi_version': (I, []),
+        'leod_backbone_create': (I, [POINTER(BackboneCfg), POINTER(VP)]),
+        'leod_backbone_layout_only': (I, [POINTER(BackboneCfg), POINTER(VP)]),
+        'leod_backbone_destroy': (None, [VP]),
+        'leod_backbone_param_info': (I, [VP, I, c_char_p, c_size_t, POINTER(c_int64), POINTER(c_int32), POINTER(c_int64 * 4)]),
+        'leod_backbone_param_count': (c_int64, [VP]),
+        'leod_backbone_bind': (I, [VP, VP, VP]),
+        'leod_backbone_prepare': (I, [VP, VP]),
+        'leod_backbone_save_bytes': (c_int64, [VP, I]),
+        'leod_backbone_reserve': (I, [VP, I]),
+        'leod_backbone_set_gemm_impl': (I, [VP, I]),
+        'leod_backbone_step_fwd': (I, [VP, VP, I, I, I, I, _VP4, _VP4, _VP4, _VP4, VP, VP]),
+        'leod_backbone_step_bwd': (I, [VP, VP, I, I, I, I, _VP4, _VP4, _VP4, _VP4, VP, _VP4, _VP4, _VP4, _VP4, VP]),
+        'leod_backbone_grads_finalize': (I, [VP, VP]),
+        'leod_gemm_nt': (I, [I, I, VP, I, VP, I, I, VP, I, VP, I, I, I, I, VP, I, VP, I, VP, I, VP]),
+        'leod_gemm_tn': (I, [I, I, VP, I, VP, I, VP, I, VP, I, I, I, VP]),
+        'leod_attention_fwd': (I, [I, VP, VP, I, I, I, I, I, I, I, I, VP]),
+        'leod_attention_bwd': (I, [I, VP, VP, VP, I, I, I, I, I, I, I, I, VP]),
+        'leod_postprocess': (I, [VP, I, I, I, F, F, I, VP, VP, I, VP]),
+        'leod_pred2label': (I, [VP, VP, I, I, I, POINTER(c_float), POINTER(c_float), I, I, VP, VP, VP]),
+        'leod_voxel_bin': (I, [VP, VP, VP, VP, c_int64, I, I, I, I, I, VP, VP]),
+        'leod_adamw_ema': (I, [VP, VP, VP, VP, VP, c_int64, I, F, F, F, F, F, F, F, VP]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)   # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return sig
+
+
+EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_backbone_create', 'leod_backbone_layout_only',
+                    'leod_backbone_destroy',
+                    'leod_backbone_param_info', 'leod_backbone_param_count', 'leod_backbone_bind', 'leod_backbone_prepare',
+                    'leod_backbone_save_bytes', 'leod_backbone_reserve', 'leod_backbone_set_gemm_impl',
+                    'leod_backbone_step_fwd', 'leod_backbone_step_bwd', 'leod_backbone_grads_finalize', 'leod_gemm_nt',
+                    'leod_gemm_tn', 'leod_attention_fwd', 'leod_attention_bwd', 'leod_postprocess', 'leod_pred2label',
+                    'leod_voxel_bin', 'leod_adamw_ema']
+
+
+def lib():
+    """Load (once) and return the shared library.  Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+                               f'or leod_b200/csrc/build.sh. There is no CPU/PyTorch fallback for the hot path.')
+        l = ctypes.CDLL(LIB_PATH)
+        _declare(l)
+        _lib = l
+    return _lib
+
+
+def check(rc, what=''):
+    if rc != 0:
+        msg = lib().leod_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'leod_b200 {what} failed ({rc}): {msg}')
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def vp4(tensors):
+    arr = _VP4()
+    for i in range(4):
+        t = tensors[i] if tensors is not None else None
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def leod_dtype(dt):
+    return {torch.float32: LEOD_F32, torch.bfloat16: LEOD_BF16, torch.uint8: LEOD_U8}[dt]

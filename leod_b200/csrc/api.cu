@@ -1,0 +1,55 @@
+// C-ABI glue: error reporting and the thin exported wrappers around the building-block kernels.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void leod_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *leod_last_error(void) { return g_err; }
+extern "C" int leod_abi_version(void) { return LEOD_ABI_VERSION; }
+
+extern "C" int leod_gemm_nt(int impl, int dtype, const void *A, int lda, const void *A2, int lda2, int K1, const void *B, int ldb,
+                            void *C, int ldc, int M, int N, int K, const float *bias, int epi, const void *R, int ldr, void *aux,
+                            int ldaux, void *stream) {
+  LEOD_REQUIRE(A && B && C, "leod_gemm_nt: null operand");
+  LEOD_REQUIRE(dtype == LEOD_F32 || dtype == LEOD_BF16, "leod_gemm_nt: dtype %d", dtype);
+  LEOD_REQUIRE(epi >= 0 && epi <= 3, "leod_gemm_nt: epilogue %d", epi);
+  GemmNT g;
+  g.A = A; g.lda = lda; g.A2 = A2; g.lda2 = lda2; g.K1 = A2 ? K1 : K;
+  g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+  g.bias = bias; g.epi = epi; g.R = R; g.ldr = ldr; g.aux = aux; g.ldaux = ldaux;
+  if (impl == 1) {
+    LEOD_REQUIRE(dtype == LEOD_BF16, "leod_gemm_nt: the tensor-core kernel takes bf16 operands");
+    return gemm_nt_tc(g, (cudaStream_t)stream);
+  }
+  return gemm_nt_simt(dtype, g, (cudaStream_t)stream);
+}
+
+extern "C" int leod_gemm_tn(int impl, int dtype, const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias,
+                            int M, int N, int K, void *stream) {
+  LEOD_REQUIRE(dY && X && dW, "leod_gemm_tn: null operand");
+  if (impl == 1) {
+    LEOD_REQUIRE(dtype == LEOD_BF16, "leod_gemm_tn: the tensor-core kernel takes bf16 operands");
+    return gemm_tn_tc(dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, (cudaStream_t)stream);
+  }
+  return gemm_tn_simt(dtype, dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, (cudaStream_t)stream);
+}
+
+extern "C" int leod_attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, int C, int dim_head, int ph, int pw,
+                                  int window, void *stream) {
+  LEOD_REQUIRE(qkv && out, "leod_attention_fwd: null operand");
+  return attention_fwd(dtype, qkv, out, B, H, W, C, dim_head, ph, pw, window, (cudaStream_t)stream);
+}
+
+extern "C" int leod_attention_bwd(int dtype, const void *qkv, const void *dout, void *dqkv, int B, int H, int W, int C,
+                                  int dim_head, int ph, int pw, int window, void *stream) {
+  LEOD_REQUIRE(qkv && dout && dqkv, "leod_attention_bwd: null operand");
+  return attention_bwd(dtype, qkv, dout, dqkv, B, H, W, C, dim_head, ph, pw, window, (cudaStream_t)stream);
+}

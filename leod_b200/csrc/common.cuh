@@ -1,0 +1,120 @@
+// Shared device/host helpers for the leod_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/leod_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+void leod_set_error(const char *fmt, ...);
+
+#define LEOD_CUDA(expr)                                                                         \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      leod_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));   \
+      return -1;                                                                                \
+    }                                                                                           \
+  } while (0)
+
+#define LEOD_REQUIRE(cond, ...)        \
+  do {                                 \
+    if (!(cond)) {                     \
+      leod_set_error(__VA_ARGS__);     \
+      return -2;                       \
+    }                                  \
+  } while (0)
+
+#define LEOD_LAUNCH_CHECK() LEOD_CUDA(cudaGetLastError())
+
+#define LEOD_TRY(expr)        \
+  do {                        \
+    int r__ = (expr);         \
+    if (r__ != 0) return r__; \
+  } while (0)
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f<uint8_t>(uint8_t v) { return (float)v; }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+static inline size_t dtype_size(int dt) { return dt == LEOD_BF16 ? 2 : (dt == LEOD_U8 ? 1 : 4); }
+
+// epilogue modes of the NT GEMM (see leod_b200.h)
+enum { EPI_NONE = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_GELU_BWD = 3 };
+
+struct GemmNT {
+  const void *A; int lda;
+  const void *A2; int lda2; int K1;
+  const void *B; int ldb;
+  void *C; int ldc;
+  int M, N, K;
+  const float *bias;
+  int epi;
+  const void *R; int ldr;
+  void *aux; int ldaux;
+};
+
+// kernels_gemm_simt.cu
+int gemm_nt_simt(int dtype, const GemmNT &g, cudaStream_t st);
+int gemm_tn_simt(int dtype, const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N,
+                 int K, cudaStream_t st);
+// kernels_gemm_tc.cu
+int gemm_nt_tc(const GemmNT &g, cudaStream_t st);
+int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N, int K,
+               cudaStream_t st);
+// kernels_attention.cu
+int attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, int C, int dh, int ph, int pw, int window,
+                  cudaStream_t st);
+int attention_bwd(int dtype, const void *qkv, const void *dout, void *dqkv, int B, int H, int W, int C, int dh, int ph,
+                  int pw, int window, cudaStream_t st);
+// kernels_elem.cu
+int layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void *y, int M, int C, float eps, cudaStream_t st);
+// dx = (dres ? dres : 0) + LN'(dy); dw += ..., db += ...
+int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, const void *dres, void *dx, float *dw, float *db,
+                  int M, int C, float eps, cudaStream_t st);
+int lstm_pointwise_fwd(int dtype, void *gates /*in: pre-act, out: activated*/, const void *c_prev, void *h_out, void *c_out,
+                       int M, int C, cudaStream_t st);
+int lstm_pointwise_bwd(int dtype, const void *gates, const void *c_prev, const void *c_out, const void *dh, const void *dh2,
+                       const void *dc, void *dgates, void *dc_prev, int M, int C, cudaStream_t st);
+int add_tensors(int dtype, const void *a, const void *b, void *out, int64_t n, cudaStream_t st);
+int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin, int xh, int xw, int Hp, int Wp, int ksz,
+                int stride, int pad, int ldcol, cudaStream_t st);
+int im2col_nhwc(int dtype, const void *x, void *col, int B, int Hi, int Wi, int Cin, int ksz, int stride, int pad, int ldcol,
+                cudaStream_t st);
+int col2im_nhwc(int dtype, const void *dcol, int ldcol, const void *dres, void *dx, int B, int Hi, int Wi, int Cin, int ksz,
+                int stride, int pad, cudaStream_t st);
+// weight preparation: dst[n, k] = scale[n] * src(n, k)  (+ transposed copy dstT[k, n])
+//   perm: 0 = src is [N, K] row-major;  1 = src is conv weight [N, Cin, kh, kw], k index = (ky*kw + kx)*Cin + cin
+int prep_weight(int dtype, const float *src, const float *scale, void *dst, int ldd, void *dstT, int lddT, int N, int K, int perm,
+                int Cin, int ksz, cudaStream_t st);
+int prep_scaled_bias(const float *b, const float *scale, float *out, int N, cudaStream_t st);
+int layerscale_grad_finalize(const float *G, const float *s, const float *W, const float *b, const float *gamma, float *dW,
+                             float *db, float *dgamma, int N, int K, cudaStream_t st);

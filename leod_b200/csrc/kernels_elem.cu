@@ -1,0 +1,400 @@
+// HBM-bound kernels of the backbone: LayerNorm, ConvLSTM gate math, patch gather/scatter for the
+// strided convolutions, weight preparation.  All are templated on the activation storage type and
+// compute in fp32.
+#include "common.cuh"
+
+namespace {
+
+constexpr int LN_MAXV = 16;  // C <= 512
+
+// ------------------------------------------------------------------ LayerNorm (one warp per token)
+template <typename T>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                     const float *__restrict__ b, T *__restrict__ y, int M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const T *xr = x + (size_t)row * C;
+  float v[LN_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = (c < C) ? to_f<T>(xr[c]) : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    const float d = (c < C) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  T *yr = y + (size_t)row * C;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C) yr[c] = from_f<T>((v[i] - mean) * rstd * w[c] + b[c]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
+                                                     const T *__restrict__ dy, const T *__restrict__ dres, T *__restrict__ dx,
+                                                     float *__restrict__ dw, float *__restrict__ db, int M, int C, float eps) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float dwacc[LN_MAXV], dbacc[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) dwacc[i] = dbacc[i] = 0.f;
+  for (int row = blockIdx.x * nwarp + warp; row < M; row += gridDim.x * nwarp) {
+    const T *xr = x + (size_t)row * C;
+    const T *gr = dy + (size_t)row * C;
+    float v[LN_MAXV], g[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = (c < C) ? to_f<T>(xr[c]) : 0.f;
+      g[i] = (c < C) ? to_f<T>(gr[c]) : 0.f;
+      s += v[i];
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      const float d = (c < C) ? v[i] - mean : 0.f;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        const float xh = (v[i] - mean) * rstd;
+        dwacc[i] += g[i] * xh;
+        dbacc[i] += g[i];
+        const float gw = g[i] * w[c];
+        v[i] = xh;   // keep xhat
+        g[i] = gw;   // keep dy*w
+        c1 += gw;
+        c2 += gw * xh;
+      }
+    }
+    c1 = warp_sum(c1) / C;
+    c2 = warp_sum(c2) / C;
+    T *dxr = dx + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        float o = rstd * (g[i] - c1 - v[i] * c2);
+        if (dres) o += to_f<T>(dres[(size_t)row * C + c]);
+        dxr[c] = from_f<T>(o);
+      }
+    }
+  }
+  // cross-warp reduction of the affine gradients, one channel slot at a time
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    if (32 * i >= C) break;
+    for (int pass = 0; pass < 2; ++pass) {
+      red[warp][lane] = pass == 0 ? dwacc[i] : dbacc[i];
+      __syncthreads();
+      if (warp == 0) {
+        float t = 0.f;
+        for (int k = 0; k < nwarp; ++k) t += red[k][lane];
+        const int c = lane + 32 * i;
+        if (c < C) atomicAdd(pass == 0 ? &dw[c] : &db[c], t);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ ConvLSTM gate math (rnn.py:57-68)
+template <typename T>
+__global__ void lstm_fwd_kernel(T *__restrict__ gates, const T *__restrict__ c_prev, T *__restrict__ h_out,
+                                T *__restrict__ c_out, int M, int C) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * C) return;
+  const int m = (int)(idx / C), c = (int)(idx % C);
+  T *gr = gates + (size_t)m * 4 * C;
+  const float f = sigmoid_f(to_f<T>(gr[c]));
+  const float i = sigmoid_f(to_f<T>(gr[C + c]));
+  const float o = sigmoid_f(to_f<T>(gr[2 * C + c]));
+  const float g = tanhf(to_f<T>(gr[3 * C + c]));
+  const float cp = c_prev ? to_f<T>(c_prev[idx]) : 0.f;
+  const float cn = f * cp + i * g;
+  gr[c] = from_f<T>(f);
+  gr[C + c] = from_f<T>(i);
+  gr[2 * C + c] = from_f<T>(o);
+  gr[3 * C + c] = from_f<T>(g);
+  c_out[idx] = from_f<T>(cn);
+  h_out[idx] = from_f<T>(o * tanhf(cn));
+}
+
+template <typename T>
+__global__ void lstm_bwd_kernel(const T *__restrict__ gates, const T *__restrict__ c_prev, const T *__restrict__ c_out,
+                                const T *__restrict__ dh, const T *__restrict__ dh2, const T *__restrict__ dc,
+                                T *__restrict__ dgates, T *__restrict__ dc_prev, int M, int C) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * C) return;
+  const int m = (int)(idx / C), c = (int)(idx % C);
+  const T *gr = gates + (size_t)m * 4 * C;
+  const float f = to_f<T>(gr[c]), i = to_f<T>(gr[C + c]), o = to_f<T>(gr[2 * C + c]), g = to_f<T>(gr[3 * C + c]);
+  const float cp = c_prev ? to_f<T>(c_prev[idx]) : 0.f;
+  const float tc = tanhf(to_f<T>(c_out[idx]));
+  float dhv = dh ? to_f<T>(dh[idx]) : 0.f;
+  if (dh2) dhv += to_f<T>(dh2[idx]);
+  float dcv = dc ? to_f<T>(dc[idx]) : 0.f;
+  dcv += dhv * o * (1.f - tc * tc);
+  T *dg = dgates + (size_t)m * 4 * C;
+  dg[c] = from_f<T>(dcv * cp * f * (1.f - f));
+  dg[C + c] = from_f<T>(dcv * g * i * (1.f - i));
+  dg[2 * C + c] = from_f<T>(dhv * tc * o * (1.f - o));
+  dg[3 * C + c] = from_f<T>(dcv * i * (1.f - g * g));
+  dc_prev[idx] = from_f<T>(dcv * f);
+}
+
+template <typename T>
+__global__ void add_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out, int64_t n) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < n) out[idx] = from_f<T>(to_f<T>(a[idx]) + to_f<T>(b[idx]));
+}
+
+// ------------------------------------------------------------------ patch gather for the strided convs
+// stem: x [B,Cin,xh,xw] channel-first (u8 / f32 / bf16), implicit zero pad to (Hp,Wp) and conv padding.
+template <typename TI, typename T>
+__global__ void im2col_nchw_kernel(const TI *__restrict__ x, T *__restrict__ col, int B, int Cin, int xh, int xw, int Ho,
+                                   int Wo, int ksz, int stride, int pad, int K, int ldcol) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo * ldcol;
+  if (idx >= total) return;
+  const int k = (int)(idx % ldcol);
+  const int64_t m = idx / ldcol;
+  float v = 0.f;
+  if (k < K) {
+    const int kx = k % ksz, ky = (k / ksz) % ksz, cin = k / (ksz * ksz);
+    const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+    if (iy >= 0 && iy < xh && ix >= 0 && ix < xw) v = to_f<TI>(x[(((size_t)b * Cin + cin) * xh + iy) * xw + ix]);
+  }
+  col[idx] = from_f<T>(v);
+}
+
+template <typename T>
+__global__ void im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ col, int B, int Hi, int Wi, int Cin, int Ho, int Wo,
+                                   int ksz, int stride, int pad, int K, int ldcol) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Ho * Wo * ldcol;
+  if (idx >= total) return;
+  const int k = (int)(idx % ldcol);
+  const int64_t m = idx / ldcol;
+  T v = from_f<T>(0.f);
+  if (k < K) {
+    const int cin = k % Cin, kx = (k / Cin) % ksz, ky = k / (Cin * ksz);
+    const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+    if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) v = x[(((size_t)b * Hi + iy) * Wi + ix) * Cin + cin];
+  }
+  col[idx] = v;
+}
+
+// gather form of the transposed patch scatter: dx[b,iy,ix,c] = dres + sum over the (<= 4) output
+// positions whose window covers (iy,ix)
+template <typename T>
+__global__ void col2im_nhwc_kernel(const T *__restrict__ dcol, int ldcol, const T *__restrict__ dres, T *__restrict__ dx, int B,
+                                   int Hi, int Wi, int Cin, int Ho, int Wo, int ksz, int stride, int pad) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * Hi * Wi * Cin;
+  if (idx >= total) return;
+  const int c = (int)(idx % Cin);
+  const int ix = (int)((idx / Cin) % Wi), iy = (int)((idx / ((int64_t)Cin * Wi)) % Hi), b = (int)(idx / ((int64_t)Cin * Wi * Hi));
+  float acc = dres ? to_f<T>(dres[idx]) : 0.f;
+  for (int ky = 0; ky < ksz; ++ky) {
+    const int ty = iy + pad - ky;
+    if (ty < 0 || ty % stride) continue;
+    const int oy = ty / stride;
+    if (oy >= Ho) continue;
+    for (int kx = 0; kx < ksz; ++kx) {
+      const int tx = ix + pad - kx;
+      if (tx < 0 || tx % stride) continue;
+      const int ox = tx / stride;
+      if (ox >= Wo) continue;
+      acc += to_f<T>(dcol[(((size_t)b * Ho + oy) * Wo + ox) * ldcol + (ky * ksz + kx) * Cin + c]);
+    }
+  }
+  dx[idx] = from_f<T>(acc);
+}
+
+// ------------------------------------------------------------------ weights
+template <typename T>
+__global__ void prep_weight_kernel(const float *__restrict__ src, const float *__restrict__ scale, T *__restrict__ dst, int ldd,
+                                   T *__restrict__ dstT, int lddT, int N, int K, int perm, int Cin, int ksz) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * K) return;
+  const int n = (int)(idx / K), k = (int)(idx % K);
+  size_t si = idx;
+  if (perm == 1) {
+    const int cin = k % Cin, kx = (k / Cin) % ksz, ky = k / (Cin * ksz);
+    si = (((size_t)n * Cin + cin) * ksz + ky) * ksz + kx;
+  }
+  float v = src[si];
+  if (scale) v *= scale[n];
+  const T t = from_f<T>(v);
+  if (dst) dst[(size_t)n * ldd + k] = t;
+  if (dstT) dstT[(size_t)k * lddT + n] = t;
+}
+
+__global__ void scaled_bias_kernel(const float *b, const float *scale, float *out, int N) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = b[i] * scale[i];
+}
+
+// y = x + gamma * (W a + b) was computed with folded weights; G = dY^T a and s = colsum(dY) are the
+// unscaled accumulators.  dW += gamma*G, db += gamma*s, dgamma += rowsum(W.G) + b*s; G,s reset.
+__global__ void ls_finalize_kernel(float *__restrict__ G, float *__restrict__ s, const float *__restrict__ W,
+                                   const float *__restrict__ b, const float *__restrict__ gamma, float *__restrict__ dW,
+                                   float *__restrict__ db, float *__restrict__ dgamma, int N, int K) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const float gm = gamma[n];
+  float dot = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float g = G[(size_t)n * K + k];
+    dot += W[(size_t)n * K + k] * g;
+    dW[(size_t)n * K + k] += gm * g;
+    G[(size_t)n * K + k] = 0.f;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    dgamma[n] += dot + b[n] * s[n];
+    db[n] += gm * s[n];
+    s[n] = 0.f;
+  }
+}
+
+inline int blocks_for(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
+
+}  // namespace
+
+#define DISPATCH_T(dtype, ...)            \
+  if ((dtype) == LEOD_F32) {              \
+    typedef float T;                      \
+    __VA_ARGS__;                          \
+  } else {                                \
+    typedef bf16 T;                       \
+    __VA_ARGS__;                          \
+  }
+
+int layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void *y, int M, int C, float eps, cudaStream_t st) {
+  LEOD_REQUIRE(C <= 32 * LN_MAXV, "layernorm: C=%d > %d", C, 32 * LN_MAXV);
+  DISPATCH_T(dtype, (ln_fwd_kernel<T><<<ceil_div(M, 8), 256, 0, st>>>((const T *)x, w, b, (T *)y, M, C, eps)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, const void *dres, void *dx, float *dw, float *db,
+                  int M, int C, float eps, cudaStream_t st) {
+  LEOD_REQUIRE(C <= 32 * LN_MAXV, "layernorm: C=%d > %d", C, 32 * LN_MAXV);
+  int blocks = ceil_div(M, 8 * 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  DISPATCH_T(dtype, (ln_bwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)x, w, (const T *)dy, (const T *)dres, (T *)dx, dw, db, M,
+                                                            C, eps)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int lstm_pointwise_fwd(int dtype, void *gates, const void *c_prev, void *h_out, void *c_out, int M, int C, cudaStream_t st) {
+  const int64_t n = (int64_t)M * C;
+  DISPATCH_T(dtype, (lstm_fwd_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((T *)gates, (const T *)c_prev, (T *)h_out, (T *)c_out, M, C)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int lstm_pointwise_bwd(int dtype, const void *gates, const void *c_prev, const void *c_out, const void *dh, const void *dh2,
+                       const void *dc, void *dgates, void *dc_prev, int M, int C, cudaStream_t st) {
+  const int64_t n = (int64_t)M * C;
+  DISPATCH_T(dtype, (lstm_bwd_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)gates, (const T *)c_prev, (const T *)c_out,
+                                                                           (const T *)dh, (const T *)dh2, (const T *)dc,
+                                                                           (T *)dgates, (T *)dc_prev, M, C)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int add_tensors(int dtype, const void *a, const void *b, void *out, int64_t n, cudaStream_t st) {
+  DISPATCH_T(dtype, (add_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)a, (const T *)b, (T *)out, n)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin, int xh, int xw, int Hp, int Wp, int ksz,
+                int stride, int pad, int ldcol, cudaStream_t st) {
+  const int Ho = (Hp + 2 * pad - ksz) / stride + 1, Wo = (Wp + 2 * pad - ksz) / stride + 1;
+  const int K = Cin * ksz * ksz;
+  const int64_t n = (int64_t)B * Ho * Wo * ldcol;
+  const int nb = blocks_for(n, 256);
+#define IM2COL_CASE(TI)                                                                                                   \
+  DISPATCH_T(dtype, (im2col_nchw_kernel<TI, T><<<nb, 256, 0, st>>>((const TI *)x, (T *)col, B, Cin, xh, xw, Ho, Wo, ksz, stride, \
+                                                                 pad, K, ldcol)))
+  if (x_dtype == LEOD_U8) {
+    IM2COL_CASE(uint8_t);
+  } else if (x_dtype == LEOD_BF16) {
+    IM2COL_CASE(bf16);
+  } else {
+    IM2COL_CASE(float);
+  }
+#undef IM2COL_CASE
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int im2col_nhwc(int dtype, const void *x, void *col, int B, int Hi, int Wi, int Cin, int ksz, int stride, int pad, int ldcol,
+                cudaStream_t st) {
+  const int Ho = (Hi + 2 * pad - ksz) / stride + 1, Wo = (Wi + 2 * pad - ksz) / stride + 1;
+  const int K = Cin * ksz * ksz;
+  const int64_t n = (int64_t)B * Ho * Wo * ldcol;
+  DISPATCH_T(dtype, (im2col_nhwc_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)x, (T *)col, B, Hi, Wi, Cin, Ho, Wo, ksz,
+                                                                              stride, pad, K, ldcol)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int col2im_nhwc(int dtype, const void *dcol, int ldcol, const void *dres, void *dx, int B, int Hi, int Wi, int Cin, int ksz,
+                int stride, int pad, cudaStream_t st) {
+  const int Ho = (Hi + 2 * pad - ksz) / stride + 1, Wo = (Wi + 2 * pad - ksz) / stride + 1;
+  const int64_t n = (int64_t)B * Hi * Wi * Cin;
+  DISPATCH_T(dtype, (col2im_nhwc_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)dcol, ldcol, (const T *)dres, (T *)dx, B,
+                                                                              Hi, Wi, Cin, Ho, Wo, ksz, stride, pad)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int prep_weight(int dtype, const float *src, const float *scale, void *dst, int ldd, void *dstT, int lddT, int N, int K, int perm,
+                int Cin, int ksz, cudaStream_t st) {
+  const int64_t n = (int64_t)N * K;
+  DISPATCH_T(dtype, (prep_weight_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>(src, scale, (T *)dst, ldd, (T *)dstT, lddT, N, K, perm,
+                                                                              Cin, ksz)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int prep_scaled_bias(const float *b, const float *scale, float *out, int N, cudaStream_t st) {
+  scaled_bias_kernel<<<blocks_for(N, 128), 128, 0, st>>>(b, scale, out, N);
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int layerscale_grad_finalize(const float *G, const float *s, const float *W, const float *b, const float *gamma, float *dW,
+                             float *db, float *dgamma, int N, int K, cudaStream_t st) {
+  ls_finalize_kernel<<<ceil_div(N, 8), 256, 0, st>>>((float *)G, (float *)s, W, b, gamma, dW, db, dgamma, N, K);
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}

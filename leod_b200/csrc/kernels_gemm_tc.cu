@@ -1,0 +1,370 @@
+// Tensor-core GEMMs for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory ->
+// tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue with fused bias / GELU / residual.
+//
+//   NT:  C[M,N] = epi(A[M,K] * B[N,K]^T + bias)      forward layers and input gradients
+//   TN:  dW[N,K] += dY[M,N]^T * X[M,K]               weight gradients (both operands MN-major)
+//
+// One 128-row output tile per CTA, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner +
+// MMA issuer (one elected lane), warps 2..5 = epilogue (one TMEM lane quarter each).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;
+constexpr int TILE_K = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int A_STAGE_BYTES = TILE_M * TILE_K * 2;
+constexpr int NUM_THREADS = 192;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a CUDA error (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B canonical layouts (cute/arch/mma_sm100_desc.hpp):
+//   bits [0,14) start address >> 4, [16,30) LBO >> 4, [32,46) SBO >> 4, [46,48) version = 1, [61,64) layout = 2
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::f16: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1),
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+struct NtArgs {
+  GemmNT g;
+  int BN;         // N tile (multiple of 16, <= 256)
+  int stages;     // smem ring depth
+  int nkb1, nkb;  // k-blocks of source 1 / total
+  int tmem_cols;  // power of two >= max(32, BN)
+};
+
+__global__ void __launch_bounds__(NUM_THREADS) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapA2,
+                                                                 const __grid_constant__ CUtensorMap mapB,
+                                                                 const __grid_constant__ CUtensorMap mapB2, const NtArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_stage_bytes = a.BN * TILE_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint64_t *bars = (uint64_t *)(smem + (size_t)a.stages * stage_bytes);
+  uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * a.stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * a.BN, m0 = blockIdx.y * TILE_M;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < a.nkb; ++kb) {
+        const int s = kb % a.stages;
+        const uint32_t ph = (kb / a.stages) & 1;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, stage_bytes);
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
+        if (kb < a.nkb1) {
+          tma_load_2d(sa, &mapA, fb, kb * TILE_K, m0);
+          tma_load_2d(sb, &mapB, fb, kb * TILE_K, n0);
+        } else {
+          tma_load_2d(sa, &mapA2, fb, (kb - a.nkb1) * TILE_K, m0);
+          tma_load_2d(sb, &mapB2, fb, (kb - a.nkb1) * TILE_K, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TILE_M, a.BN, 0, 0);
+      for (int kb = 0; kb < a.nkb; ++kb) {
+        const int s = kb % a.stages;
+        const uint32_t ph = (kb / a.stages) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
+        const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < TILE_K / 16; ++k) {
+          // +32 bytes per 16-element K step inside the 128B swizzle row (>>4 encoded: +2)
+          tc_mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        tc_commit(smem_u32(&empty_bar[s]));
+      }
+      tc_commit(smem_u32(tmem_full));
+    }
+  } else {
+    // epilogue: TMEM lane quarter = warp % 4, one accumulator row per thread
+    const int quarter = warp & 3;
+    const int m = m0 + quarter * 32 + lane;
+    mbar_wait(smem_u32(tmem_full), 0);
+    tc_fence_after();
+    const GemmNT &g = a.g;
+    const bool row_ok = m < g.M;
+    for (int c = 0; c < a.BN; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+      const int n = n0 + c;
+      if (!row_ok || n >= g.N) continue;
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      const int nvalid = min(16, g.N - n);
+      if (g.bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) v[j] += g.bias[n + j];
+      }
+      if (nvalid == 16) {
+        if (g.epi == EPI_GELU) {
+          bf16 *ax = (bf16 *)g.aux + (size_t)m * g.ldaux + n;
+          __align__(16) bf16 t[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            t[j] = __float2bfloat16_rn(v[j]);
+            v[j] = gelu_f(v[j]);
+          }
+          ((uint4 *)ax)[0] = ((uint4 *)t)[0];
+          ((uint4 *)ax)[1] = ((uint4 *)t)[1];
+        } else if (g.epi == EPI_RESID) {
+          const bf16 *rx = (const bf16 *)g.R + (size_t)m * g.ldr + n;
+          __align__(16) bf16 t[16];
+          ((uint4 *)t)[0] = ((const uint4 *)rx)[0];
+          ((uint4 *)t)[1] = ((const uint4 *)rx)[1];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(t[j]);
+        } else if (g.epi == EPI_GELU_BWD) {
+          const bf16 *ax = (const bf16 *)g.aux + (size_t)m * g.ldaux + n;
+          __align__(16) bf16 t[16];
+          ((uint4 *)t)[0] = ((const uint4 *)ax)[0];
+          ((uint4 *)t)[1] = ((const uint4 *)ax)[1];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= gelu_grad_f(__bfloat162float(t[j]));
+        }
+        __align__(16) bf16 o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = __float2bfloat16_rn(v[j]);
+        bf16 *cx = (bf16 *)g.C + (size_t)m * g.ldc + n;
+        ((uint4 *)cx)[0] = ((uint4 *)o)[0];
+        ((uint4 *)cx)[1] = ((uint4 *)o)[1];
+      } else {
+        for (int j = 0; j < nvalid; ++j) {
+          float x = v[j];
+          if (g.epi == EPI_GELU) {
+            ((bf16 *)g.aux)[(size_t)m * g.ldaux + n + j] = __float2bfloat16_rn(x);
+            x = gelu_f(x);
+          } else if (g.epi == EPI_RESID) {
+            x += __bfloat162float(((const bf16 *)g.R)[(size_t)m * g.ldr + n + j]);
+          } else if (g.epi == EPI_GELU_BWD) {
+            x *= gelu_grad_f(__bfloat162float(((const bf16 *)g.aux)[(size_t)m * g.ldaux + n + j]));
+          }
+          ((bf16 *)g.C)[(size_t)m * g.ldc + n + j] = __float2bfloat16_rn(x);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ tensor maps
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void *ptr;
+  uint64_t inner, outer, ld;
+  uint32_t box_inner, box_outer;
+  bool operator<(const MapKey &o) const {
+    return std::tie(ptr, inner, outer, ld, box_inner, box_outer) <
+           std::tie(o.ptr, o.inner, o.outer, o.ld, o.box_inner, o.box_outer);
+  }
+};
+
+// 2D bf16 tensor map: `inner` contiguous elements per row, `outer` rows, row pitch `ld` elements.
+int make_map(CUtensorMap *out, const void *ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+             uint32_t box_outer) {
+  static std::map<MapKey, CUtensorMap> cache;
+  static std::mutex mu;
+  MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  auto fn = get_encode_fn();
+  LEOD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+  LEOD_REQUIRE(((uintptr_t)ptr & 15) == 0, "TMA operand %p is not 16-byte aligned", ptr);
+  LEOD_REQUIRE((ld * 2) % 16 == 0, "TMA operand row pitch %llu elements is not a multiple of 8", (unsigned long long)ld);
+  LEOD_REQUIRE(box_inner * 2 <= 128 && box_outer <= 256, "TMA box %ux%u out of range", box_inner, box_outer);
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LEOD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (ptr %p dims %llux%llu ld %llu box %ux%u)", (int)r, ptr,
+               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return 0;
+}
+
+int pick_bn(int N) {
+  if (N <= 256) return (int)round_up(N, 16);
+  for (int bn = 256; bn >= 64; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 128;
+}
+
+}  // namespace
+
+int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
+  if (g.M <= 0 || g.N <= 0) return 0;
+  LEOD_REQUIRE(g.K > 0, "gemm_nt_tc: K = %d", g.K);
+  LEOD_REQUIRE(g.ldc % 8 == 0 && (!g.R || g.ldr % 8 == 0) && (!g.aux || g.ldaux % 8 == 0),
+               "gemm_nt_tc: output/residual pitches must be multiples of 8 elements");
+  LEOD_REQUIRE((((uintptr_t)g.C) & 15) == 0, "gemm_nt_tc: C not 16-byte aligned");
+  NtArgs a;
+  a.g = g;
+  a.BN = pick_bn(g.N);
+  const int K1 = g.A2 ? g.K1 : g.K, K2 = g.K - K1;
+  LEOD_REQUIRE(K1 > 0 && K2 >= 0 && (K2 == 0 || K1 % 8 == 0), "gemm_nt_tc: bad K split %d/%d", K1, g.K);
+  a.nkb1 = ceil_div(K1, TILE_K);
+  a.nkb = a.nkb1 + (K2 > 0 ? ceil_div(K2, TILE_K) : 0);
+  a.stages = a.nkb < 4 ? a.nkb : 4;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.BN) a.tmem_cols *= 2;
+  CUtensorMap mA, mA2, mB, mB2;
+  LEOD_TRY(make_map(&mA, g.A, K1, g.M, g.lda, TILE_K, TILE_M));
+  LEOD_TRY(make_map(&mB, g.B, K1, g.N, g.ldb, TILE_K, a.BN));
+  if (K2 > 0) {
+    LEOD_TRY(make_map(&mA2, g.A2, K2, g.M, g.lda2, TILE_K, TILE_M));
+    LEOD_TRY(make_map(&mB2, (const bf16 *)g.B + K1, K2, g.N, g.ldb, TILE_K, a.BN));
+  } else {
+    mA2 = mA;
+    mB2 = mB;
+  }
+  const int stage_bytes = A_STAGE_BYTES + a.BN * TILE_K * 2;
+  const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + (2 * a.stages + 2) * 8;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    smem_set = 200 * 1024;
+  }
+  dim3 grid(ceil_div(g.N, a.BN), ceil_div(g.M, TILE_M));
+  gemm_nt_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N, int K,
+               cudaStream_t st) {
+  // weight-gradient GEMM: the tcgen05 MN-major version is staged behind this entry point; until it
+  // is enabled the bf16 operands go through the SIMT kernel (fp32 accumulate, same results).
+  return gemm_tn_simt(LEOD_BF16, dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, st);
+}
