@@ -27,6 +27,14 @@ enum { LEOD_F32 = 0, LEOD_BF16 = 1, LEOD_U8 = 2 };
 
 const char *leod_last_error(void);
 int leod_abi_version(void);
+/* Kernels launched by this library so far in this process. */
+unsigned long long leod_launch_count(void);
+/* Per-kernel-class timing with CUDA events on the launching stream (measurement aid for bench.py;
+ * off by default).  Kinds: 0 gemm_nt, 1 gemm_tn, 2 attention fwd, 3 attention bwd, 4 layernorm,
+ * 5 lstm gates, 6 patch gather/scatter, 7 other.  collect(): out[kind*4 + {0,1,2,3}] = launches,
+ * total ms, algorithmic FLOPs, algorithmic bytes since the last collect. */
+int leod_profile_enable(int on);
+int leod_profile_collect(double *out, int n_kinds);
 
 /* ------------------------------------------------------------------ recurrent backbone
  * Replaces models/detection/recurrent_backbone/maxvit_rnn.py:23-115 (RNNDetector) and everything

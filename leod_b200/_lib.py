@@ -30,6 +30,9 @@ def _declare(lib):
     sig = {
         'leod_last_error': (c_char_p, []),
         'leod_abi_version': (I, []),
+        'leod_launch_count': (ctypes.c_ulonglong, []),
+        'leod_profile_enable': (I, [I]),
+        'leod_profile_collect': (I, [POINTER(ctypes.c_double), I]),
         'leod_backbone_create': (I, [POINTER(BackboneCfg), POINTER(VP)]),
         'leod_backbone_layout_only': (I, [POINTER(BackboneCfg), POINTER(VP)]),
         'leod_backbone_destroy': (None, [VP]),
@@ -59,7 +62,8 @@ def _declare(lib):
     return sig
 
 
-EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_backbone_create', 'leod_backbone_layout_only',
+EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 'leod_profile_enable',
+                    'leod_profile_collect', 'leod_backbone_create', 'leod_backbone_layout_only',
                     'leod_backbone_destroy',
                     'leod_backbone_param_info', 'leod_backbone_param_count', 'leod_backbone_bind', 'leod_backbone_prepare',
                     'leod_backbone_save_bytes', 'leod_backbone_reserve', 'leod_backbone_set_gemm_impl',
@@ -102,6 +106,18 @@ def vp4(tensors):
         t = tensors[i] if tensors is not None else None
         arr[i] = None if t is None else t.data_ptr()
     return arr
+
+
+PROF_KINDS = ['gemm_nt', 'gemm_tn', 'attention_fwd', 'attention_bwd', 'layernorm', 'lstm_gates', 'patch', 'other']
+
+
+def profile_collect():
+    """-> {kind: dict(launches, ms, flops, bytes)} since the last call (needs leod_profile_enable(1))."""
+    n = len(PROF_KINDS)
+    buf = (ctypes.c_double * (4 * n))()
+    check(lib().leod_profile_collect(buf, n), 'profile_collect')
+    return {k: dict(launches=int(buf[4 * i]), ms=buf[4 * i + 1], flops=buf[4 * i + 2], bytes=buf[4 * i + 3])
+            for i, k in enumerate(PROF_KINDS)}
 
 
 def leod_dtype(dt):

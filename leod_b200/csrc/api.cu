@@ -12,6 +12,53 @@ void leod_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+unsigned long long g_leod_launches = 0;
+
+// ------------------------------------------------------------------ event profiler
+#include <vector>
+namespace {
+struct ProfRec { int kind; cudaEvent_t e0, e1; double flops, bytes; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t st_) : slot(-1), st(st_) {
+  if (!g_prof_on) return;
+  ProfRec r;
+  r.kind = kind; r.flops = flops; r.bytes = bytes;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+  slot = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
+}
+
+extern "C" int leod_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+// out[kind*4 + {0,1,2,3}] = {launches, total ms, algorithmic flops, algorithmic bytes}; clears the log.
+extern "C" int leod_profile_collect(double *out, int n_kinds) {
+  LEOD_REQUIRE(out && n_kinds >= PK_COUNT, "leod_profile_collect: need room for %d kinds", (int)PK_COUNT);
+  for (int i = 0; i < n_kinds * 4; ++i) out[i] = 0.0;
+  for (auto &r : g_prof) {
+    float ms = 0.f;
+    LEOD_CUDA(cudaEventSynchronize(r.e1));
+    LEOD_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    out[r.kind * 4 + 0] += 1;
+    out[r.kind * 4 + 1] += ms;
+    out[r.kind * 4 + 2] += r.flops;
+    out[r.kind * 4 + 3] += r.bytes;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return 0;
+}
+extern "C" unsigned long long leod_launch_count(void) { return g_leod_launches; }
+
 extern "C" const char *leod_last_error(void) { return g_err; }
 extern "C" int leod_abi_version(void) { return LEOD_ABI_VERSION; }
 

@@ -28,7 +28,21 @@ void leod_set_error(const char *fmt, ...);
     }                                  \
   } while (0)
 
-#define LEOD_LAUNCH_CHECK() LEOD_CUDA(cudaGetLastError())
+extern unsigned long long g_leod_launches;  // kernels launched by this library (gpu_launches in bench.py)
+#define LEOD_LAUNCH_CHECK()        \
+  do {                             \
+    ++g_leod_launches;             \
+    LEOD_CUDA(cudaGetLastError()); \
+  } while (0)
+
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline pass).
+enum ProfKind { PK_GEMM_NT = 0, PK_GEMM_TN, PK_ATTN_FWD, PK_ATTN_BWD, PK_LAYERNORM, PK_LSTM, PK_PATCH, PK_OTHER, PK_COUNT };
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  ProfScope(int kind, double flops, double bytes, cudaStream_t st);
+  ~ProfScope();
+};
 
 #define LEOD_TRY(expr)        \
   do {                        \

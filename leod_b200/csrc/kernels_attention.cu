@@ -148,6 +148,7 @@ int attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, in
   LEOD_REQUIRE(smem <= 200 * 1024, "attention: partition of %d tokens needs %zu B of shared memory", Tn, smem);
   const float scale = 1.0f / sqrtf((float)dh);
   dim3 grid(groups, heads);
+  ProfScope ps(PK_ATTN_FWD, 4.0 * groups * heads * Tn * Tn * dh, 4.0 * B * H * W * C * dtype_size(dtype), st);
   if (dtype == LEOD_F32) {
     LEOD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_fwd_kernel<float><<<grid, ATT_THREADS, smem, st>>>((const float *)qkv, (float *)out, H, W, C, dh, ph, pw, window, scale);
@@ -168,6 +169,7 @@ int attention_bwd(int dtype, const void *qkv, const void *dout, void *dqkv, int 
   LEOD_REQUIRE(smem <= 200 * 1024, "attention: partition of %d tokens needs %zu B of shared memory", Tn, smem);
   const float scale = 1.0f / sqrtf((float)dh);
   dim3 grid(groups, heads);
+  ProfScope ps(PK_ATTN_BWD, 10.0 * groups * heads * Tn * Tn * dh, 7.0 * B * H * W * C * dtype_size(dtype), st);
   if (dtype == LEOD_F32) {
     LEOD_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_bwd_kernel<float><<<grid, ATT_THREADS, smem, st>>>((const float *)qkv, (const float *)dout, (float *)dqkv, H, W, C, dh,

@@ -294,6 +294,7 @@ inline int blocks_for(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
   }
 
 int layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void *y, int M, int C, float eps, cudaStream_t st) {
+  ProfScope ps(PK_LAYERNORM, 8.0 * M * C, 2.0 * M * C * dtype_size(dtype), st);
   LEOD_REQUIRE(C <= 32 * LN_MAXV, "layernorm: C=%d > %d", C, 32 * LN_MAXV);
   DISPATCH_T(dtype, (ln_fwd_kernel<T><<<ceil_div(M, 8), 256, 0, st>>>((const T *)x, w, b, (T *)y, M, C, eps)));
   LEOD_LAUNCH_CHECK();
@@ -302,6 +303,7 @@ int layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void
 
 int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, const void *dres, void *dx, float *dw, float *db,
                   int M, int C, float eps, cudaStream_t st) {
+  ProfScope ps(PK_LAYERNORM, 16.0 * M * C, (dres ? 4.0 : 3.0) * M * C * dtype_size(dtype), st);
   LEOD_REQUIRE(C <= 32 * LN_MAXV, "layernorm: C=%d > %d", C, 32 * LN_MAXV);
   int blocks = ceil_div(M, 8 * 8);
   if (blocks > 148 * 4) blocks = 148 * 4;
@@ -313,6 +315,7 @@ int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, cons
 }
 
 int lstm_pointwise_fwd(int dtype, void *gates, const void *c_prev, void *h_out, void *c_out, int M, int C, cudaStream_t st) {
+  ProfScope ps(PK_LSTM, 30.0 * M * C, 11.0 * M * C * dtype_size(dtype), st);
   const int64_t n = (int64_t)M * C;
   DISPATCH_T(dtype, (lstm_fwd_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((T *)gates, (const T *)c_prev, (T *)h_out, (T *)c_out, M, C)));
   LEOD_LAUNCH_CHECK();
@@ -321,6 +324,7 @@ int lstm_pointwise_fwd(int dtype, void *gates, const void *c_prev, void *h_out, 
 
 int lstm_pointwise_bwd(int dtype, const void *gates, const void *c_prev, const void *c_out, const void *dh, const void *dh2,
                        const void *dc, void *dgates, void *dc_prev, int M, int C, cudaStream_t st) {
+  ProfScope ps(PK_LSTM, 30.0 * M * C, 13.0 * M * C * dtype_size(dtype), st);
   const int64_t n = (int64_t)M * C;
   DISPATCH_T(dtype, (lstm_bwd_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)gates, (const T *)c_prev, (const T *)c_out,
                                                                            (const T *)dh, (const T *)dh2, (const T *)dc,
@@ -330,6 +334,7 @@ int lstm_pointwise_bwd(int dtype, const void *gates, const void *c_prev, const v
 }
 
 int add_tensors(int dtype, const void *a, const void *b, void *out, int64_t n, cudaStream_t st) {
+  ProfScope ps(PK_OTHER, 0.0, 3.0 * n * dtype_size(dtype), st);
   DISPATCH_T(dtype, (add_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)a, (const T *)b, (T *)out, n)));
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -337,6 +342,7 @@ int add_tensors(int dtype, const void *a, const void *b, void *out, int64_t n, c
 
 int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin, int xh, int xw, int Hp, int Wp, int ksz,
                 int stride, int pad, int ldcol, cudaStream_t st) {
+  ProfScope ps(PK_PATCH, 0.0, (double)B * (Hp / stride) * (Wp / stride) * ldcol * dtype_size(dtype) + (double)B * Cin * xh * xw * dtype_size(x_dtype), st);
   const int Ho = (Hp + 2 * pad - ksz) / stride + 1, Wo = (Wp + 2 * pad - ksz) / stride + 1;
   const int K = Cin * ksz * ksz;
   const int64_t n = (int64_t)B * Ho * Wo * ldcol;
@@ -358,6 +364,7 @@ int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin
 
 int im2col_nhwc(int dtype, const void *x, void *col, int B, int Hi, int Wi, int Cin, int ksz, int stride, int pad, int ldcol,
                 cudaStream_t st) {
+  ProfScope ps(PK_PATCH, 0.0, ((double)B * (Hi / stride) * (Wi / stride) * ldcol + (double)B * Hi * Wi * Cin) * dtype_size(dtype), st);
   const int Ho = (Hi + 2 * pad - ksz) / stride + 1, Wo = (Wi + 2 * pad - ksz) / stride + 1;
   const int K = Cin * ksz * ksz;
   const int64_t n = (int64_t)B * Ho * Wo * ldcol;
@@ -369,6 +376,7 @@ int im2col_nhwc(int dtype, const void *x, void *col, int B, int Hi, int Wi, int 
 
 int col2im_nhwc(int dtype, const void *dcol, int ldcol, const void *dres, void *dx, int B, int Hi, int Wi, int Cin, int ksz,
                 int stride, int pad, cudaStream_t st) {
+  ProfScope ps(PK_PATCH, 0.0, ((double)B * (Hi / stride) * (Wi / stride) * ldcol + (double)B * Hi * Wi * Cin) * dtype_size(dtype), st);
   const int Ho = (Hi + 2 * pad - ksz) / stride + 1, Wo = (Wi + 2 * pad - ksz) / stride + 1;
   const int64_t n = (int64_t)B * Hi * Wi * Cin;
   DISPATCH_T(dtype, (col2im_nhwc_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)dcol, ldcol, (const T *)dres, (T *)dx, B,

@@ -1,0 +1,202 @@
+"""Training / evaluation step loops.  Mirror of modules/detection.py:24 (class Module):
+`training_step` (:150-298), `_val_test_step_impl` (:300-401), `configure_optimizers` (:485-518),
+`load_weight` (:583-594), on the same batch-dict contract (data/utils/types.py:15-32).
+
+pytorch_lightning is optional: when it is importable the class derives from pl.LightningModule and
+plugs into the reference's train.py / val.py unchanged; otherwise it is a plain nn.Module driven by
+bench.py / the tests.  Logging, visualisation and the Prophesee evaluator are out of scope
+ — `training_step` returns the same {'loss': ...} (+ 'log_dict').
+"""
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from leod_b200.data.utils.types import DataType, dget
+from leod_b200.models.detection.yolox.utils.boxes import postprocess
+from leod_b200.models.detection.yolox_extension.models.detector import YoloXDetector
+from .utils.detection import DATA_KEY, WORKER_ID_KEY, BackboneFeatureSelector, Mode, RNNStates, mode_2_string
+from .utils.ssod import fused_adamw_ema
+
+try:  # pragma: no cover - not installed in the build image
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+except Exception:  # noqa: BLE001
+    _Base = nn.Module
+
+
+def get_subsample_label_idx(L: int, use_every: int = -1, remove_every: int = -1):
+    """modules/utils/ssod.py:19-37."""
+    assert use_every == -1 or remove_every == -1
+    all_idx = list(range(L))
+    if use_every == 1:
+        return tuple(all_idx)
+    if use_every > 0:
+        use_idx = all_idx[1::use_every]
+    elif remove_every > 0:
+        use_idx = sorted(set(all_idx) - set(all_idx[::remove_every]))
+    else:
+        raise ValueError('Either use_every or remove_every must be > 0')
+    if L - 1 not in use_idx:
+        use_idx.append(L - 1)
+    return tuple(use_idx)
+
+
+class Module(_Base):
+    def __init__(self, full_config, ssod: bool = False):
+        super().__init__()
+        self.full_config = full_config
+        self.mdl_config = full_config.model
+        self.num_classes = self.mdl_config.head.num_classes
+        self.mdl = YoloXDetector(self.mdl_config, ssod=ssod)
+        self.dst_config = full_config.get('dataset', None) if hasattr(full_config, 'get') else None
+        L = self.dst_config.sequence_length if self.dst_config is not None else 1
+        self.label_subsample_idx = get_subsample_label_idx(L=L, use_every=self.mdl_config.get('use_label_every', 1))
+        self.mode_2_rnn_states: Dict[Mode, RNNStates] = {m: RNNStates() for m in Mode}
+        self._opt_state = None
+
+    # ------------------------------------------------------------------ data
+    def get_data_from_batch(self, batch: Any):
+        """modules/detection.py:129-148.  The uint8 -> float cast and the zero padding to
+        `in_res_hw` are fused into the stem's patch loader, so tensors pass through untouched."""
+        return batch[DATA_KEY]
+
+    # ------------------------------------------------------------------ train
+    def training_step(self, batch: Any, batch_idx: int = 0, log: bool = False):
+        data = self.get_data_from_batch(batch)
+        worker_id = batch[WORKER_ID_KEY]
+        mode = Mode.TRAIN
+        ev_seq = dget(data, DataType.EV_REPR)
+        sparse_obj_labels = dget(data, DataType.OBJLABELS_SEQ)
+        is_first_sample = dget(data, DataType.IS_FIRST_SAMPLE)
+        self.mode_2_rnn_states[mode].reset(worker_id=worker_id, indices_or_bool_tensor=is_first_sample)
+        L = len(ev_seq)
+        assert L > 0
+        B = len(sparse_obj_labels[0])
+        prev_states = self.mode_2_rnn_states[mode].get_states(worker_id=worker_id)
+        selector = BackboneFeatureSelector()
+        obj_labels = []
+        ignore = self.mdl_config.get('ignore_image', False)
+        ignore_label = self.mdl_config.head.get('ignore_label', 1024)
+        for tidx in range(L):
+            feats, states = self.mdl.forward_backbone(x=ev_seq[tidx], previous_states=prev_states, token_mask=None)
+            prev_states = states
+            current_labels, valid_idx = sparse_obj_labels[tidx].get_valid_labels_and_batch_indices(
+                ignore=ignore, ignore_label=ignore_label)
+            if len(current_labels) > 0:
+                selector.add_backbone_features(backbone_features=feats,
+                                               selected_indices=None if len(valid_idx) == B and valid_idx == list(range(B)) else valid_idx)
+                obj_labels.extend(current_labels)
+        self.mode_2_rnn_states[mode].save_states_and_detach(worker_id=worker_id, states=prev_states)
+        assert len(obj_labels) > 0
+        sel = selector.get_batched_backbone_features()
+        labels_yolox = type(obj_labels[0]).get_labels_as_batched_tensor(obj_label_list=obj_labels, format_='yolox')
+        labels_yolox = labels_yolox.to(device=ev_seq[0].device, dtype=torch.float32)
+        predictions, losses = self.mdl.forward_detect(backbone_features=sel, targets=labels_yolox)
+        assert losses is not None and 'loss' in losses
+        out = {'loss': losses['loss']}
+        prefix = f'{mode_2_string[mode]}/'
+        out['log_dict'] = {f'{prefix}{k}': v for k, v in losses.items()}
+        out['predictions'] = predictions
+        return out
+
+    # ------------------------------------------------------------------ eval
+    @torch.inference_mode()
+    def _val_test_step_impl(self, batch: Any, mode: Mode = Mode.VAL):
+        """modules/detection.py:300-401 without the evaluator buffer: returns the post-processed
+        predictions of the labelled frames and the labels."""
+        data = self.get_data_from_batch(batch)
+        worker_id = batch[WORKER_ID_KEY]
+        ev_seq = dget(data, DataType.EV_REPR)
+        sparse_obj_labels = dget(data, DataType.OBJLABELS_SEQ)
+        is_first_sample = dget(data, DataType.IS_FIRST_SAMPLE)
+        self.mode_2_rnn_states[mode].reset(worker_id=worker_id, indices_or_bool_tensor=is_first_sample)
+        prev_states = self.mode_2_rnn_states[mode].get_states(worker_id=worker_id)
+        selector = BackboneFeatureSelector()
+        obj_labels = []
+        for tidx in range(len(ev_seq)):
+            feats, states = self.mdl.forward_backbone(x=ev_seq[tidx], previous_states=prev_states)
+            prev_states = states
+            current_labels, valid_idx = sparse_obj_labels[tidx].get_valid_labels_and_batch_indices()
+            if len(current_labels) > 0:
+                selector.add_backbone_features(backbone_features=feats, selected_indices=valid_idx)
+                obj_labels.extend(current_labels)
+        self.mode_2_rnn_states[mode].save_states_and_detach(worker_id=worker_id, states=prev_states)
+        if len(obj_labels) == 0:
+            return {'skip': True}
+        predictions, _ = self.mdl.forward_detect(backbone_features=selector.get_batched_backbone_features())
+        pp = self.mdl_config.postprocess
+        pred_processed = postprocess(prediction=predictions, num_classes=self.num_classes,
+                                     conf_thre=pp.confidence_threshold, nms_thre=pp.nms_threshold)
+        return {'labels': obj_labels, 'predictions': pred_processed, 'skip': False}
+
+    def validation_step(self, batch, batch_idx=0):
+        return self._val_test_step_impl(batch, Mode.VAL)
+
+    def test_step(self, batch, batch_idx=0):
+        return self._val_test_step_impl(batch, Mode.TEST)
+
+    # ------------------------------------------------------------------ optimisation
+    def configure_optimizers(self):
+        """modules/detection.py:485-518: AdamW(lr, weight_decay) + OneCycleLR (linear anneal)."""
+        tc = self.full_config.training
+        opt = torch.optim.AdamW(self.mdl.parameters(), lr=tc.learning_rate, weight_decay=tc.get('weight_decay', 0))
+        sched = tc.get('lr_scheduler', None)
+        if sched is None or not sched.get('use', False):
+            return opt
+        total = sched.total_steps if hasattr(sched, 'total_steps') else tc.max_steps
+        s = torch.optim.lr_scheduler.OneCycleLR(optimizer=opt, max_lr=tc.learning_rate, div_factor=sched.div_factor,
+                                                final_div_factor=sched.final_div_factor, total_steps=total,
+                                                pct_start=sched.pct_start, cycle_momentum=False, anneal_strategy='linear')
+        return {'optimizer': opt, 'lr_scheduler': {'scheduler': s, 'interval': 'step', 'frequency': 1, 'strict': True}}
+
+    def load_weight(self, ckpt_path: str, strict: bool = True):
+        """modules/detection.py:583-594: raw state dict or {'state_dict': ...}."""
+        ckpt = torch.load(ckpt_path, map_location='cpu')
+        if 'state_dict' in ckpt:
+            ckpt = ckpt['state_dict']
+        self.load_state_dict(ckpt, strict=strict)
+
+
+class FlatOptimizer:
+    """AdamW + clip-by-value (+ optional teacher EMA) over the model's flat parameter buffers: one
+    kernel launch per buffer per step (leod_adamw_ema) instead of ~4 launches x 376 tensors."""
+
+    def __init__(self, detector: YoloXDetector, lr: float, weight_decay: float = 0.0, clip_value: float = 1.0,
+                 betas=(0.9, 0.999), eps: float = 1e-8, ema: bool = False, ema_alpha: float = 0.999):
+        self.detector = detector
+        self.lr, self.wd, self.clip, self.betas, self.eps = lr, weight_decay, clip_value, betas, eps
+        self.step_count = 0
+        self.ema_alpha = ema_alpha
+        bb = detector.backbone
+        rest = [p for n, p in detector.named_parameters() if not n.startswith('backbone.')]
+        self.rest = rest
+        dev = bb.flat_params.device
+        n = sum(p.numel() for p in rest)
+        self.rest_flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.rest_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in rest:
+                k = p.numel()
+                self.rest_flat[off:off + k].copy_(p.reshape(-1))
+                p.data = self.rest_flat[off:off + k].view(p.shape)
+                p.grad = self.rest_grad[off:off + k].view(p.shape)
+                off += k
+        self.bufs = [(bb.flat_params, bb.flat_grads), (self.rest_flat, self.rest_grad)]
+        self.m = [torch.zeros_like(p) for p, _ in self.bufs]
+        self.v = [torch.zeros_like(p) for p, _ in self.bufs]
+        self.ema = [p.clone() for p, _ in self.bufs] if ema else [None, None]
+
+    def zero_grad(self):
+        for _, g in self.bufs:
+            g.zero_()
+
+    def step(self, lr: Optional[float] = None):
+        from .utils.ssod import ema_alpha_at
+        self.step_count += 1
+        a = ema_alpha_at(self.step_count - 1, self.ema_alpha)
+        for (p, g), m, v, e in zip(self.bufs, self.m, self.v, self.ema):
+            fused_adamw_ema(p, g, m, v, step=self.step_count, lr=self.lr if lr is None else lr, beta1=self.betas[0],
+                            beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, clip_value=self.clip, ema=e, ema_alpha=a)
+        self.detector.backbone.mark_params_updated()

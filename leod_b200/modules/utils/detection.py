@@ -1,0 +1,83 @@
+"""State / feature book-keeping of the step loops.  Mirror of modules/utils/detection.py:11-14
+(Mode), :27-58 (BackboneFeatureSelector), :95-157 (RNNStates) — same method names and semantics
+(states keyed by dataloader worker id, partial reset in place, detach between batches)."""
+from enum import Enum, auto
+from typing import Dict, List, Optional, Union
+
+import torch as th
+
+WORKER_ID_KEY = 'worker_id'
+DATA_KEY = 'data'
+
+
+class Mode(Enum):
+    TRAIN = auto()
+    VAL = auto()
+    TEST = auto()
+
+
+mode_2_string = {Mode.TRAIN: 'train', Mode.VAL: 'val', Mode.TEST: 'test'}
+
+
+class BackboneFeatureSelector:
+    """Collect the rows of the per-timestep features that have labels; concatenate over time."""
+
+    def __init__(self):
+        self.features: Optional[Dict[int, List[th.Tensor]]] = None
+
+    def reset(self):
+        self.features = None
+
+    def add_backbone_features(self, backbone_features: Dict[int, th.Tensor], selected_indices: Optional[List[int]] = None):
+        if selected_indices is not None:
+            assert len(selected_indices) > 0
+        if self.features is None:
+            self.features = {k: [] for k in backbone_features}
+        for k, v in backbone_features.items():
+            self.features[k].append(v[selected_indices] if selected_indices is not None else v)
+
+    def get_batched_backbone_features(self) -> Optional[Dict[int, th.Tensor]]:
+        if self.features is None:
+            return None
+        return {k: th.cat(v, dim=0) for k, v in self.features.items()}
+
+
+class RNNStates:
+    def __init__(self):
+        self.states = {}
+
+    @classmethod
+    def recursive_detach(cls, inp):
+        if isinstance(inp, th.Tensor):
+            return inp.detach()
+        if isinstance(inp, (list, tuple)):
+            return type(inp)(cls.recursive_detach(x) for x in inp)
+        if isinstance(inp, dict):
+            return {k: cls.recursive_detach(v) for k, v in inp.items()}
+        raise NotImplementedError
+
+    @classmethod
+    def recursive_reset(cls, inp, indices_or_bool_tensor=None):
+        if isinstance(inp, th.Tensor):
+            assert inp.requires_grad is False
+            if indices_or_bool_tensor is None:
+                inp[:] = 0
+            else:
+                assert len(indices_or_bool_tensor) > 0
+                inp[indices_or_bool_tensor] = 0
+            return inp
+        if isinstance(inp, (list, tuple)):
+            return type(inp)(cls.recursive_reset(x, indices_or_bool_tensor) for x in inp)
+        if isinstance(inp, dict):
+            return {k: cls.recursive_reset(v, indices_or_bool_tensor) for k, v in inp.items()}
+        raise NotImplementedError
+
+    def save_states_and_detach(self, worker_id: int, states) -> None:
+        self.states[worker_id] = self.recursive_detach(states)
+
+    def get_states(self, worker_id: int):
+        return self.states.get(worker_id, None)
+
+    def reset(self, worker_id: int, indices_or_bool_tensor: Optional[Union[List[int], th.Tensor]] = None):
+        if worker_id in self.states:
+            self.states[worker_id] = self.recursive_reset(self.states[worker_id], indices_or_bool_tensor)

@@ -1,0 +1,152 @@
+"""Parity of the CUDA backbone (through the reference-facing module interface -> C ABI) against the
+golden fixtures generated from the reference, and against the oracle at the full BASELINE sizes."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_net_fixture, rel_err
+from test_host_cpu import product_cfg
+
+pytestmark = pytest.mark.gpu
+
+TOL = {'fp32': 2e-4, 'bf16': 2.5e-2}
+GRAD_TOL = {'fp32': 1e-3, 'bf16': 6e-2}
+
+
+@pytest.fixture(scope='module')
+def net():
+    return load_net_fixture()
+
+
+def build(cfg, sd, hw, dtype, thr=None, gemm_impl=None):
+    from leod_b200.models.detection.yolox_extension.models.detector import YoloXDetector
+    m = YoloXDetector(product_cfg(cfg, hw, ignore_thresh=thr, compute_dtype=dtype))
+    m.load_state_dict(sd)
+    m.cuda()
+    if gemm_impl is not None:
+        m.backbone.set_gemm_impl(gemm_impl)
+    return m
+
+
+@pytest.mark.parametrize('dtype,impl', [('fp32', None), ('bf16', 0), ('bf16', 1)])
+def test_eval_unroll_matches_reference_fixture(net, dtype, impl):
+    z, cfg, sd, d = net
+    m = build(cfg, sd, (d['H'], d['W']), dtype, gemm_impl=impl).eval()
+    x = torch.from_numpy(z['x']).cuda()          # uint8, like the dataloader delivers it
+    states = None
+    worst = 0.0
+    with torch.inference_mode():
+        for t in range(d['T']):
+            feats, states = m.forward_backbone(x[t], states)
+            for s in (1, 2, 3, 4):
+                assert tuple(feats[s].shape) == tuple(z[f'eval/feat{s}_t{t}'].shape)
+                e = rel_err(feats[s].float().cpu(), z[f'eval/feat{s}_t{t}'])
+                worst = max(worst, e)
+                assert e < TOL[dtype], (dtype, impl, s, t, e)
+        for s in range(4):
+            assert rel_err(states[s][1].float().cpu(), z[f'eval/c{s}']) < TOL[dtype]
+        preds, _ = m.forward_detect(feats)
+    assert rel_err(preds.cpu(), z['eval/preds']) < TOL[dtype]
+    print(f'[{dtype}/{impl}] worst feature error {worst:.2e}')
+
+
+@pytest.mark.parametrize('dtype,impl', [('fp32', None), ('bf16', 0), ('bf16', 1)])
+@pytest.mark.parametrize('tag,thr', [('plain', None), ('ignore', None)])
+def test_train_step_losses_and_grads_match_reference_fixture(net, dtype, impl, tag, thr):
+    z, cfg, sd, d = net
+    m = build(cfg, sd, (d['H'], d['W']), dtype, thr, gemm_impl=impl).train()
+    x = torch.from_numpy(z['x']).cuda().float()
+    states = None
+    for t in range(d['T']):
+        feats, states = m.forward_backbone(x[t], states)
+    preds, losses = m.forward_detect(feats, targets=torch.from_numpy(z[f'train_{tag}/labels']).cuda())
+    for k in ('loss', 'iou_loss', 'conf_loss', 'cls_loss'):
+        ref = float(z[f'train_{tag}/{k}'])
+        assert abs(float(losses[k]) - ref) < (1e-3 if dtype == 'fp32' else 5e-2) * max(1.0, abs(ref)), (k, float(losses[k]), ref)
+    losses['loss'].backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    for key in z.files:
+        if key.startswith(f'train_{tag}/grad/'):
+            name = key.split('/grad/')[1]
+            assert grads[name] is not None, name
+            e = rel_err(grads[name].float().cpu(), z[key])
+            assert e < GRAD_TOL[dtype], (dtype, impl, name, e)
+
+
+def test_gradient_accumulation_and_zero_grad(net):
+    z, cfg, sd, d = net
+    m = build(cfg, sd, (d['H'], d['W']), 'fp32').train()
+    x = torch.from_numpy(z['x']).cuda().float()
+    lab = torch.from_numpy(z['train_plain/labels']).cuda()
+
+    def run():
+        states = None
+        for t in range(2):
+            feats, states = m.forward_backbone(x[t], states)
+        _, losses = m.forward_detect(feats, targets=lab)
+        losses['loss'].backward()
+
+    w = m.backbone.stages[1].lstm.conv1x1.weight
+    run()
+    g1 = w.grad.clone()
+    run()                                   # accumulates
+    assert rel_err(w.grad, 2 * g1) < 1e-5
+    m.zero_grad(set_to_none=True)
+    run()                                   # starts again from zero
+    assert rel_err(w.grad, g1) < 1e-5
+
+
+def test_state_reset_and_detach_contract(net):
+    """modules/utils/detection.py:95-157: the caller zeroes rows of detached states in place."""
+    z, cfg, sd, d = net
+    m = build(cfg, sd, (d['H'], d['W']), 'fp32').eval()
+    x = torch.from_numpy(z['x']).cuda()
+    with torch.no_grad():
+        _, states = m.forward_backbone(x[0], None)
+        states = [(h.detach(), c.detach()) for h, c in states]
+        for h, c in states:
+            h[1] = 0
+            c[1] = 0
+        f_a, _ = m.forward_backbone(x[1], states)
+        f_b, _ = m.forward_backbone(x[1][1:2], None)     # sample 1 alone, fresh state
+    assert rel_err(f_a[4][1:2].float(), f_b[4].float()) < 1e-4
+
+
+@pytest.mark.parametrize('size,dataset,B', [('small', 'gen1', 2), ('base', 'gen4', 1), ('tiny', 'gen1', 1)])
+def test_full_size_matches_oracle(size, dataset, B):
+    """BASELINE configs' real shapes (RVT-S Gen1 256x320, RVT-B Gen4 384x640): CUDA vs the CPU oracle
+    on seeded inputs, two timesteps, bf16 path within 1e-2-class tolerance and fp32 path within 1e-3."""
+    from oracle import rvt, yolox
+    from oracle.config import ModelCfg
+    from leod_b200.config import DATASETS, make_model_cfg
+    from leod_b200.models.detection.yolox_extension.models.detector import YoloXDetector
+    torch.manual_seed(0)
+    ocfg = ModelCfg.named(size, dataset)
+    fh, fw = DATASETS[dataset]['frame_hw']
+    x = ((torch.rand(2, B, 20, fh, fw) < 0.1).float() * torch.randint(1, 6, (2, B, 20, fh, fw))).to(torch.uint8)
+    ref = None
+    for dtype in ('fp32', 'bf16'):
+        m = YoloXDetector(make_model_cfg(size=size, dataset=dataset, compute_dtype=dtype))
+        if ref is None:
+            with torch.no_grad():   # make LayerScale matter (init is 1e-5)
+                for k, p in m.named_parameters():
+                    if k.endswith('gamma'):
+                        p.fill_(0.5)
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+            states = None
+            with torch.no_grad():
+                for t in range(2):
+                    feats, states = rvt.backbone_forward(rvt.pad_input(x[t], DATASETS[dataset]['in_res_hw']), states, sd, ocfg)
+                ref = (feats, yolox.detect_forward(feats, sd, ocfg)[0])
+        else:
+            m.load_state_dict(sd)
+        m.cuda().eval()
+        states = None
+        with torch.inference_mode():
+            for t in range(2):
+                feats, states = m.forward_backbone(x[t].cuda(), states)
+            preds, _ = m.forward_detect(feats)
+        for s in (1, 2, 3, 4):
+            assert rel_err(feats[s].float().cpu(), ref[0][s]) < (1e-3 if dtype == 'fp32' else 2.5e-2), (dtype, s)
+        assert rel_err(preds.cpu(), ref[1]) < (1e-3 if dtype == 'fp32' else 2.5e-2)
