@@ -161,6 +161,7 @@ def main():
     ap.add_argument('--gemm-impl', type=int, default=None, help='0 SIMT, 1 tcgen05 (debug)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-kinds', action='store_true', help='print the per-kernel-class breakdown to stderr')
+    ap.add_argument('--profile-csv', default=None, help='write one line per launch of the roofline pass to this CSV')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -266,10 +267,13 @@ def main():
     roof = None
     if rank == 0:
         lib.leod_profile_enable(1)
+        if args.profile_csv:
+            lib.leod_profile_csv(args.profile_csv.encode())
         train_step(*resident[0])
         torch.cuda.synchronize()
         kinds = _lib.profile_collect()
         lib.leod_profile_enable(0)
+        lib.leod_profile_csv(None)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))

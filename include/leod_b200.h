@@ -34,7 +34,11 @@ unsigned long long leod_launch_count(void);
  * 5 lstm gates, 6 patch gather/scatter, 7 other.  collect(): out[kind*4 + {0,1,2,3}] = launches,
  * total ms, algorithmic FLOPs, algorithmic bytes since the last collect. */
 int leod_profile_enable(int on);
+/* Debug: route bf16 attention through the SIMT kernel instead of the tensor-core one. */
+int leod_debug_force_simt_attention(int on);
 int leod_profile_collect(double *out, int n_kinds);
+/* Additionally log every launch (kind,us,flops,bytes,d0,d1,d2) to a CSV file at the next collect; NULL closes it. */
+int leod_profile_csv(const char *path);
 
 /* ------------------------------------------------------------------ recurrent backbone
  * Replaces models/detection/recurrent_backbone/maxvit_rnn.py:23-115 (RNNDetector) and everything
@@ -119,6 +123,19 @@ int leod_attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int 
                        int window, void *stream);
 int leod_attention_bwd(int dtype, const void *qkv, const void *dout, void *dqkv, int B, int H, int W, int C, int dim_head,
                        int ph, int pw, int window, void *stream);
+
+/* LayerNorm over the channel dimension of a token matrix (layers/norm.py:44-56 -> F.layer_norm) and its
+ * backward: dx = (dres ? dres : 0) + dLN(dy); dw += sum dy*xhat; db += sum dy (fp32 accumulators). */
+int leod_layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void *y, int M, int C, float eps,
+                       void *stream);
+int leod_layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, const void *dres, void *dx, float *dw,
+                       float *db, int M, int C, float eps, void *stream);
+/* ConvLSTM gate math (models/layers/rnn.py:57-68).  gates [M,4C] = pre-activations (f|i|o|g) on entry,
+ * activations on exit; c_prev may be NULL (zero state).  Backward: dh2 is an optional second gradient
+ * w.r.t. h that is added to dh. */
+int leod_lstm_gates_fwd(int dtype, void *gates, const void *c_prev, void *h_out, void *c_out, int M, int C, void *stream);
+int leod_lstm_gates_bwd(int dtype, const void *gates, const void *c_prev, const void *c_out, const void *dh, const void *dh2,
+                        const void *dc, void *dgates, void *dc_prev, int M, int C, void *stream);
 
 /* ------------------------------------------------------------------ detection post-processing
  * Replaces models/detection/yolox/utils/boxes.py:32-86 (postprocess) including the

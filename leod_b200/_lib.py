@@ -32,6 +32,8 @@ def _declare(lib):
         'leod_abi_version': (I, []),
         'leod_launch_count': (ctypes.c_ulonglong, []),
         'leod_profile_enable': (I, [I]),
+        'leod_debug_force_simt_attention': (I, [I]),
+        'leod_profile_csv': (I, [c_char_p]),
         'leod_profile_collect': (I, [POINTER(ctypes.c_double), I]),
         'leod_backbone_create': (I, [POINTER(BackboneCfg), POINTER(VP)]),
         'leod_backbone_layout_only': (I, [POINTER(BackboneCfg), POINTER(VP)]),
@@ -50,6 +52,10 @@ def _declare(lib):
         'leod_gemm_tn': (I, [I, I, VP, I, VP, I, VP, I, VP, I, I, I, VP]),
         'leod_attention_fwd': (I, [I, VP, VP, I, I, I, I, I, I, I, I, VP]),
         'leod_attention_bwd': (I, [I, VP, VP, VP, I, I, I, I, I, I, I, I, VP]),
+        'leod_layernorm_fwd': (I, [I, VP, VP, VP, VP, I, I, F, VP]),
+        'leod_layernorm_bwd': (I, [I, VP, VP, VP, VP, VP, VP, VP, I, I, F, VP]),
+        'leod_lstm_gates_fwd': (I, [I, VP, VP, VP, VP, I, I, VP]),
+        'leod_lstm_gates_bwd': (I, [I, VP, VP, VP, VP, VP, VP, VP, VP, I, I, VP]),
         'leod_postprocess': (I, [VP, I, I, I, F, F, I, VP, VP, I, VP]),
         'leod_pred2label': (I, [VP, VP, I, I, I, POINTER(c_float), POINTER(c_float), I, I, VP, VP, VP]),
         'leod_voxel_bin': (I, [VP, VP, VP, VP, c_int64, I, I, I, I, I, VP, VP]),
@@ -62,13 +68,14 @@ def _declare(lib):
     return sig
 
 
-EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 'leod_profile_enable',
+EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 'leod_profile_enable', 'leod_debug_force_simt_attention', 'leod_profile_csv',
                     'leod_profile_collect', 'leod_backbone_create', 'leod_backbone_layout_only',
                     'leod_backbone_destroy',
                     'leod_backbone_param_info', 'leod_backbone_param_count', 'leod_backbone_bind', 'leod_backbone_prepare',
                     'leod_backbone_save_bytes', 'leod_backbone_reserve', 'leod_backbone_set_gemm_impl',
                     'leod_backbone_step_fwd', 'leod_backbone_step_bwd', 'leod_backbone_grads_finalize', 'leod_gemm_nt',
-                    'leod_gemm_tn', 'leod_attention_fwd', 'leod_attention_bwd', 'leod_postprocess', 'leod_pred2label',
+                    'leod_gemm_tn', 'leod_attention_fwd', 'leod_attention_bwd', 'leod_layernorm_fwd', 'leod_layernorm_bwd',
+                    'leod_lstm_gates_fwd', 'leod_lstm_gates_bwd', 'leod_postprocess', 'leod_pred2label',
                     'leod_voxel_bin', 'leod_adamw_ema']
 
 

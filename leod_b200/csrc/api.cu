@@ -17,15 +17,16 @@ unsigned long long g_leod_launches = 0;
 // ------------------------------------------------------------------ event profiler
 #include <vector>
 namespace {
-struct ProfRec { int kind; cudaEvent_t e0, e1; double flops, bytes; };
+struct ProfRec { int kind; cudaEvent_t e0, e1; double flops, bytes; int d[3]; };
+FILE *g_prof_csv = nullptr;
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 }  // namespace
 
-ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t st_) : slot(-1), st(st_) {
+ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t st_, int d0, int d1, int d2) : slot(-1), st(st_) {
   if (!g_prof_on) return;
   ProfRec r;
-  r.kind = kind; r.flops = flops; r.bytes = bytes;
+  r.kind = kind; r.flops = flops; r.bytes = bytes; r.d[0] = d0; r.d[1] = d1; r.d[2] = d2;
   if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
   cudaEventRecord(r.e0, st);
   g_prof.push_back(r);
@@ -51,10 +52,21 @@ extern "C" int leod_profile_collect(double *out, int n_kinds) {
     out[r.kind * 4 + 1] += ms;
     out[r.kind * 4 + 2] += r.flops;
     out[r.kind * 4 + 3] += r.bytes;
+    if (g_prof_csv) fprintf(g_prof_csv, "%d,%.3f,%.0f,%.0f,%d,%d,%d\n", r.kind, ms * 1e3, r.flops, r.bytes, r.d[0], r.d[1], r.d[2]);
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
   }
   g_prof.clear();
+  return 0;
+}
+// Also write one CSV line per launch (kind,us,flops,bytes,d0,d1,d2) at the next collect; NULL stops.
+extern "C" int leod_profile_csv(const char *path) {
+  if (g_prof_csv) fclose(g_prof_csv);
+  g_prof_csv = path ? fopen(path, "w") : nullptr;
+  return (path && !g_prof_csv) ? -1 : 0;
+}
+extern "C" int leod_debug_force_simt_attention(int on) {
+  g_attention_force_simt = on;
   return 0;
 }
 extern "C" unsigned long long leod_launch_count(void) { return g_leod_launches; }
@@ -99,4 +111,24 @@ extern "C" int leod_attention_bwd(int dtype, const void *qkv, const void *dout, 
                                   int dim_head, int ph, int pw, int window, void *stream) {
   LEOD_REQUIRE(qkv && dout && dqkv, "leod_attention_bwd: null operand");
   return attention_bwd(dtype, qkv, dout, dqkv, B, H, W, C, dim_head, ph, pw, window, (cudaStream_t)stream);
+}
+
+extern "C" int leod_layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void *y, int M, int C, float eps,
+                                  void *stream) {
+  LEOD_REQUIRE(x && w && b && y, "leod_layernorm_fwd: null operand");
+  return layernorm_fwd(dtype, x, w, b, y, M, C, eps, (cudaStream_t)stream);
+}
+extern "C" int leod_layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, const void *dres, void *dx, float *dw,
+                                  float *db, int M, int C, float eps, void *stream) {
+  LEOD_REQUIRE(x && w && dy && dx && dw && db, "leod_layernorm_bwd: null operand");
+  return layernorm_bwd(dtype, x, w, dy, dres, dx, dw, db, M, C, eps, (cudaStream_t)stream);
+}
+extern "C" int leod_lstm_gates_fwd(int dtype, void *gates, const void *c_prev, void *h_out, void *c_out, int M, int C, void *stream) {
+  LEOD_REQUIRE(gates && h_out && c_out, "leod_lstm_gates_fwd: null operand");
+  return lstm_pointwise_fwd(dtype, gates, c_prev, h_out, c_out, M, C, (cudaStream_t)stream);
+}
+extern "C" int leod_lstm_gates_bwd(int dtype, const void *gates, const void *c_prev, const void *c_out, const void *dh,
+                                   const void *dh2, const void *dc, void *dgates, void *dc_prev, int M, int C, void *stream) {
+  LEOD_REQUIRE(gates && c_out && dgates && dc_prev, "leod_lstm_gates_bwd: null operand");
+  return lstm_pointwise_bwd(dtype, gates, c_prev, c_out, dh, dh2, dc, dgates, dc_prev, M, C, (cudaStream_t)stream);
 }

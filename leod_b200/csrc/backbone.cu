@@ -153,13 +153,13 @@ int gemm_nt(leod_backbone *h, const GemmNT &g, cudaStream_t st) {
   const double e = (double)h->esz();
   double bytes = e * ((double)g.M * g.K + (double)g.N * g.K + (double)g.M * g.N);
   if (g.epi == EPI_GELU || g.epi == EPI_RESID || g.epi == EPI_GELU_BWD) bytes += e * (double)g.M * g.N;
-  ProfScope ps(PK_GEMM_NT, 2.0 * g.M * g.N * g.K, bytes, st);
+  ProfScope ps(PK_GEMM_NT, 2.0 * g.M * g.N * g.K, bytes, st, g.M, g.N, g.K);
   if (h->gemm_impl == 1 && h->cfg.dtype == LEOD_BF16) return gemm_nt_tc(g, st);
   return gemm_nt_simt(h->cfg.dtype, g, st);
 }
 int gemm_tn(leod_backbone *h, const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N,
             int K, cudaStream_t st) {
-  ProfScope ps(PK_GEMM_TN, 2.0 * M * N * K, (double)h->esz() * ((double)M * N + (double)M * K) + 8.0 * N * K, st);
+  ProfScope ps(PK_GEMM_TN, 2.0 * M * N * K, (double)h->esz() * ((double)M * N + (double)M * K) + 8.0 * N * K, st, M, N, K);
   if (h->gemm_impl == 1 && h->cfg.dtype == LEOD_BF16) return gemm_tn_tc(dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, st);
   return gemm_tn_simt(h->cfg.dtype, dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, st);
 }

@@ -40,7 +40,7 @@ enum ProfKind { PK_GEMM_NT = 0, PK_GEMM_TN, PK_ATTN_FWD, PK_ATTN_BWD, PK_LAYERNO
 struct ProfScope {
   int slot;
   cudaStream_t st;
-  ProfScope(int kind, double flops, double bytes, cudaStream_t st);
+  ProfScope(int kind, double flops, double bytes, cudaStream_t st, int d0 = 0, int d1 = 0, int d2 = 0);
   ~ProfScope();
 };
 
@@ -109,6 +109,11 @@ int attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, in
                   cudaStream_t st);
 int attention_bwd(int dtype, const void *qkv, const void *dout, void *dqkv, int B, int H, int W, int C, int dh, int ph,
                   int pw, int window, cudaStream_t st);
+// kernels_attention_tc.cu (bf16, mma.sync): return 1 when the shape has no instantiation
+int attention_fwd_tc(const void *qkv, void *out, int B, int H, int W, int C, int dh, int ph, int pw, int window, cudaStream_t st);
+int attention_bwd_tc(const void *qkv, const void *dout, void *dqkv, int B, int H, int W, int C, int dh, int ph, int pw, int window,
+                     cudaStream_t st);
+extern int g_attention_force_simt;
 // kernels_elem.cu
 int layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void *y, int M, int C, float eps, cudaStream_t st);
 // dx = (dres ? dres : 0) + LN'(dy); dw += ..., db += ...

@@ -139,10 +139,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const T *__restri
 
 }  // namespace
 
+int g_attention_force_simt = 0;
+
 int attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, int C, int dh, int ph, int pw, int window,
                   cudaStream_t st) {
   LEOD_REQUIRE(H % ph == 0 && W % pw == 0, "attention: %dx%d not divisible by partition %dx%d", H, W, ph, pw);
   LEOD_REQUIRE(C % dh == 0, "attention: C=%d not divisible by dim_head=%d", C, dh);
+  if (dtype == LEOD_BF16 && !g_attention_force_simt) {
+    const int rc = attention_fwd_tc(qkv, out, B, H, W, C, dh, ph, pw, window, st);
+    if (rc <= 0) return rc;  // 1 = no tensor-core instantiation for this (tokens, dim_head)
+  }
   const int Tn = ph * pw, groups = B * (H / ph) * (W / pw), heads = C / dh;
   const size_t smem = sizeof(float) * (3 * Tn * (dh + 1) + Tn * (Tn + 1)) + sizeof(int) * Tn;
   LEOD_REQUIRE(smem <= 200 * 1024, "attention: partition of %d tokens needs %zu B of shared memory", Tn, smem);
@@ -164,6 +170,10 @@ int attention_bwd(int dtype, const void *qkv, const void *dout, void *dqkv, int 
                   int window, cudaStream_t st) {
   LEOD_REQUIRE(H % ph == 0 && W % pw == 0, "attention: %dx%d not divisible by partition %dx%d", H, W, ph, pw);
   LEOD_REQUIRE(C % dh == 0, "attention: C=%d not divisible by dim_head=%d", C, dh);
+  if (dtype == LEOD_BF16 && !g_attention_force_simt) {
+    const int rc = attention_bwd_tc(qkv, dout, dqkv, B, H, W, C, dh, ph, pw, window, st);
+    if (rc <= 0) return rc;
+  }
   const int Tn = ph * pw, groups = B * (H / ph) * (W / pw), heads = C / dh;
   const size_t smem = sizeof(float) * (4 * Tn * (dh + 1) + 2 * Tn * (Tn + 1)) + sizeof(int) * Tn;
   LEOD_REQUIRE(smem <= 200 * 1024, "attention: partition of %d tokens needs %zu B of shared memory", Tn, smem);

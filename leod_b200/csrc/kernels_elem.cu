@@ -1,14 +1,16 @@
 // HBM-bound kernels of the backbone: LayerNorm, ConvLSTM gate math, patch gather/scatter for the
 // strided convolutions, weight preparation.  All are templated on the activation storage type and
 // compute in fp32.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int LN_MAXV = 16;  // C <= 512
+constexpr int LN_MAX_C = 512;
 
 // ------------------------------------------------------------------ LayerNorm (one warp per token)
-template <typename T>
+template <typename T, int LN_MAXV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
                                                      const float *__restrict__ b, T *__restrict__ y, int M, int C, float eps) {
   const int lane = threadIdx.x & 31;
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const T *__restrict__ x, co
   }
 }
 
-template <typename T>
+template <typename T, int LN_MAXV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
                                                      const T *__restrict__ dy, const T *__restrict__ dres, T *__restrict__ dx,
                                                      float *__restrict__ dw, float *__restrict__ db, int M, int C, float eps) {
@@ -169,67 +171,116 @@ __global__ void add_kernel(const T *__restrict__ a, const T *__restrict__ b, T *
 
 // ------------------------------------------------------------------ patch gather for the strided convs
 // stem: x [B,Cin,xh,xw] channel-first (u8 / f32 / bf16), implicit zero pad to (Hp,Wp) and conv padding.
+// One thread produces 8 consecutive patch entries (one 16-byte store for bf16); the k -> (cin,ky,kx)
+// decomposition comes from a shared-memory table instead of per-element divisions.
 template <typename TI, typename T>
-__global__ void im2col_nchw_kernel(const TI *__restrict__ x, T *__restrict__ col, int B, int Cin, int xh, int xw, int Ho,
-                                   int Wo, int ksz, int stride, int pad, int K, int ldcol) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * Ho * Wo * ldcol;
-  if (idx >= total) return;
-  const int k = (int)(idx % ldcol);
-  const int64_t m = idx / ldcol;
-  float v = 0.f;
-  if (k < K) {
+__global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI *__restrict__ x, T *__restrict__ col, int B, int Cin, int xh,
+                                                          int xw, int Ho, int Wo, int ksz, int stride, int pad, int K, int ldcol) {
+  extern __shared__ int ktab[];  // per k: (cin*xh*xw + ky*xw + kx) << 8 | ky << 4 | kx
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
     const int kx = k % ksz, ky = (k / ksz) % ksz, cin = k / (ksz * ksz);
-    const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
-    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-    if (iy >= 0 && iy < xh && ix >= 0 && ix < xw) v = to_f<TI>(x[(((size_t)b * Cin + cin) * xh + iy) * xw + ix]);
+    ktab[k] = ((cin * xh * xw + ky * xw + kx) << 8) | (ky << 4) | kx;
   }
-  col[idx] = from_f<T>(v);
+  __syncthreads();
+  const int chunks = ldcol / 8;
+  const int64_t total = (int64_t)B * Ho * Wo * chunks;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % chunks);
+    const int64_t m = idx / chunks;
+    const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+    const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
+    const TI *base = x + (size_t)b * Cin * xh * xw + (int64_t)iy0 * xw + ix0;
+    __align__(16) T vals[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = ch * 8 + j;
+      float v = 0.f;
+      if (k < K) {
+        const int e = ktab[k];
+        const int iy = iy0 + ((e >> 4) & 15), ix = ix0 + (e & 15);
+        if (iy >= 0 && iy < xh && ix >= 0 && ix < xw) v = to_f<TI>(base[e >> 8]);
+      }
+      vals[j] = from_f<T>(v);
+    }
+    T *dst = col + (size_t)m * ldcol + ch * 8;
+    if (sizeof(T) == 2) {
+      *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(vals);
+    } else {
+      reinterpret_cast<uint4 *>(dst)[0] = reinterpret_cast<const uint4 *>(vals)[0];
+      reinterpret_cast<uint4 *>(dst)[1] = reinterpret_cast<const uint4 *>(vals)[1];
+    }
+  }
 }
 
+// stages 2-4: x [B,Hi,Wi,Cin] channels-last; 8 channels (16 bytes in bf16) per thread
 template <typename T>
-__global__ void im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ col, int B, int Hi, int Wi, int Cin, int Ho, int Wo,
-                                   int ksz, int stride, int pad, int K, int ldcol) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * Ho * Wo * ldcol;
-  if (idx >= total) return;
-  const int k = (int)(idx % ldcol);
-  const int64_t m = idx / ldcol;
-  T v = from_f<T>(0.f);
-  if (k < K) {
-    const int cin = k % Cin, kx = (k / Cin) % ksz, ky = k / (Cin * ksz);
-    const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
-    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
-    if (iy >= 0 && iy < Hi && ix >= 0 && ix < Wi) v = x[(((size_t)b * Hi + iy) * Wi + ix) * Cin + cin];
+__global__ void __launch_bounds__(256) im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ col, int B, int Hi, int Wi,
+                                                          int Cin, int Ho, int Wo, int ksz, int stride, int pad, int K, int ldcol) {
+  const int cchunks = Cin / 8, chunks = ldcol / 8;
+  const int64_t total = (int64_t)B * Ho * Wo * chunks;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % chunks);
+    const int64_t m = idx / chunks;
+    T *dst = col + (size_t)m * ldcol + ch * 8;
+    const int tap = ch / cchunks, c8 = ch % cchunks;
+    bool ok = ch * 8 < K;
+    const T *src = nullptr;
+    if (ok) {
+      const int kx = tap % ksz, ky = tap / ksz;
+      const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
+      const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+      ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Wi;
+      src = x + (((size_t)b * Hi + iy) * Wi + ix) * Cin + c8 * 8;
+    }
+    constexpr int NV = sizeof(T) * 8 / 16;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      reinterpret_cast<uint4 *>(dst)[v] = ok ? reinterpret_cast<const uint4 *>(src)[v] : make_uint4(0, 0, 0, 0);
   }
-  col[idx] = v;
 }
 
 // gather form of the transposed patch scatter: dx[b,iy,ix,c] = dres + sum over the (<= 4) output
 // positions whose window covers (iy,ix)
 template <typename T>
-__global__ void col2im_nhwc_kernel(const T *__restrict__ dcol, int ldcol, const T *__restrict__ dres, T *__restrict__ dx, int B,
-                                   int Hi, int Wi, int Cin, int Ho, int Wo, int ksz, int stride, int pad) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)B * Hi * Wi * Cin;
-  if (idx >= total) return;
-  const int c = (int)(idx % Cin);
-  const int ix = (int)((idx / Cin) % Wi), iy = (int)((idx / ((int64_t)Cin * Wi)) % Hi), b = (int)(idx / ((int64_t)Cin * Wi * Hi));
-  float acc = dres ? to_f<T>(dres[idx]) : 0.f;
-  for (int ky = 0; ky < ksz; ++ky) {
-    const int ty = iy + pad - ky;
-    if (ty < 0 || ty % stride) continue;
-    const int oy = ty / stride;
-    if (oy >= Ho) continue;
-    for (int kx = 0; kx < ksz; ++kx) {
-      const int tx = ix + pad - kx;
-      if (tx < 0 || tx % stride) continue;
-      const int ox = tx / stride;
-      if (ox >= Wo) continue;
-      acc += to_f<T>(dcol[(((size_t)b * Ho + oy) * Wo + ox) * ldcol + (ky * ksz + kx) * Cin + c]);
+__global__ void __launch_bounds__(256) col2im_nhwc_kernel(const T *__restrict__ dcol, int ldcol, const T *__restrict__ dres,
+                                                          T *__restrict__ dx, int B, int Hi, int Wi, int Cin, int Ho, int Wo, int ksz,
+                                                          int stride, int pad) {
+  const int cchunks = Cin / 8;
+  const int64_t total = (int64_t)B * Hi * Wi * cchunks;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % cchunks);
+    const int ix = (int)((idx / cchunks) % Wi), iy = (int)((idx / ((int64_t)cchunks * Wi)) % Hi),
+              b = (int)(idx / ((int64_t)cchunks * Wi * Hi));
+    float acc[8];
+    const size_t o = (((size_t)b * Hi + iy) * Wi + ix) * Cin + c8 * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = dres ? to_f<T>(dres[o + j]) : 0.f;
+    for (int ky = 0; ky < ksz; ++ky) {
+      const int ty = iy + pad - ky;
+      if (ty < 0 || ty % stride) continue;
+      const int oy = ty / stride;
+      if (oy >= Ho) continue;
+      for (int kx = 0; kx < ksz; ++kx) {
+        const int tx = ix + pad - kx;
+        if (tx < 0 || tx % stride) continue;
+        const int ox = tx / stride;
+        if (ox >= Wo) continue;
+        const T *src = dcol + (((size_t)b * Ho + oy) * Wo + ox) * ldcol + (ky * ksz + kx) * Cin + c8 * 8;
+        __align__(16) T v[8];
+        constexpr int NV = sizeof(T) * 8 / 16;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) reinterpret_cast<uint4 *>(v)[q] = reinterpret_cast<const uint4 *>(src)[q];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += to_f<T>(v[j]);
+      }
     }
+    __align__(16) T outv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) outv[j] = from_f<T>(acc[j]);
+    constexpr int NV = sizeof(T) * 8 / 16;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) reinterpret_cast<uint4 *>(dx + o)[q] = reinterpret_cast<const uint4 *>(outv)[q];
   }
-  dx[idx] = from_f<T>(acc);
 }
 
 // ------------------------------------------------------------------ weights
@@ -294,22 +345,31 @@ inline int blocks_for(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
   }
 
 int layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void *y, int M, int C, float eps, cudaStream_t st) {
-  ProfScope ps(PK_LAYERNORM, 8.0 * M * C, 2.0 * M * C * dtype_size(dtype), st);
-  LEOD_REQUIRE(C <= 32 * LN_MAXV, "layernorm: C=%d > %d", C, 32 * LN_MAXV);
-  DISPATCH_T(dtype, (ln_fwd_kernel<T><<<ceil_div(M, 8), 256, 0, st>>>((const T *)x, w, b, (T *)y, M, C, eps)));
+  ProfScope ps(PK_LAYERNORM, 8.0 * M * C, 2.0 * M * C * dtype_size(dtype), st, M, C, 0);
+  LEOD_REQUIRE(C <= LN_MAX_C, "layernorm: C=%d > %d", C, LN_MAX_C);
+#define LN_FWD(NV) DISPATCH_T(dtype, (ln_fwd_kernel<T, NV><<<ceil_div(M, 8), 256, 0, st>>>((const T *)x, w, b, (T *)y, M, C, eps)))
+  const int nv = ceil_div(C, 32);
+  if (nv <= 1) { LN_FWD(1); } else if (nv <= 2) { LN_FWD(2); } else if (nv <= 3) { LN_FWD(3); } else if (nv <= 4) { LN_FWD(4); }
+  else if (nv <= 6) { LN_FWD(6); } else if (nv <= 8) { LN_FWD(8); } else if (nv <= 12) { LN_FWD(12); } else { LN_FWD(16); }
+#undef LN_FWD
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 
 int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, const void *dres, void *dx, float *dw, float *db,
                   int M, int C, float eps, cudaStream_t st) {
-  ProfScope ps(PK_LAYERNORM, 16.0 * M * C, (dres ? 4.0 : 3.0) * M * C * dtype_size(dtype), st);
-  LEOD_REQUIRE(C <= 32 * LN_MAXV, "layernorm: C=%d > %d", C, 32 * LN_MAXV);
-  int blocks = ceil_div(M, 8 * 8);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  ProfScope ps(PK_LAYERNORM, 16.0 * M * C, (dres ? 4.0 : 3.0) * M * C * dtype_size(dtype), st, M, C, 1);
+  LEOD_REQUIRE(C <= LN_MAX_C, "layernorm: C=%d > %d", C, LN_MAX_C);
+  int blocks = ceil_div(M, 8);          // one row per warp until the grid covers the GPU a few times over
+  if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  DISPATCH_T(dtype, (ln_bwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)x, w, (const T *)dy, (const T *)dres, (T *)dx, dw, db, M,
-                                                            C, eps)));
+#define LN_BWD(NV)                                                                                                             \
+  DISPATCH_T(dtype, (ln_bwd_kernel<T, NV><<<blocks, 256, 0, st>>>((const T *)x, w, (const T *)dy, (const T *)dres, (T *)dx, dw, db, \
+                                                                  M, C, eps)))
+  const int nv = ceil_div(C, 32);
+  if (nv <= 1) { LN_BWD(1); } else if (nv <= 2) { LN_BWD(2); } else if (nv <= 3) { LN_BWD(3); } else if (nv <= 4) { LN_BWD(4); }
+  else if (nv <= 6) { LN_BWD(6); } else if (nv <= 8) { LN_BWD(8); } else if (nv <= 12) { LN_BWD(12); } else { LN_BWD(16); }
+#undef LN_BWD
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -342,14 +402,18 @@ int add_tensors(int dtype, const void *a, const void *b, void *out, int64_t n, c
 
 int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin, int xh, int xw, int Hp, int Wp, int ksz,
                 int stride, int pad, int ldcol, cudaStream_t st) {
-  ProfScope ps(PK_PATCH, 0.0, (double)B * (Hp / stride) * (Wp / stride) * ldcol * dtype_size(dtype) + (double)B * Cin * xh * xw * dtype_size(x_dtype), st);
+  ProfScope ps(PK_PATCH, 0.0, (double)B * (Hp / stride) * (Wp / stride) * ldcol * dtype_size(dtype) + (double)B * Cin * xh * xw * dtype_size(x_dtype), st, B, Cin, 0);
   const int Ho = (Hp + 2 * pad - ksz) / stride + 1, Wo = (Wp + 2 * pad - ksz) / stride + 1;
   const int K = Cin * ksz * ksz;
-  const int64_t n = (int64_t)B * Ho * Wo * ldcol;
-  const int nb = blocks_for(n, 256);
-#define IM2COL_CASE(TI)                                                                                                   \
-  DISPATCH_T(dtype, (im2col_nchw_kernel<TI, T><<<nb, 256, 0, st>>>((const TI *)x, (T *)col, B, Cin, xh, xw, Ho, Wo, ksz, stride, \
-                                                                 pad, K, ldcol)))
+  LEOD_REQUIRE(ldcol % 8 == 0 && ksz <= 15 && K * sizeof(int) <= 40 * 1024 && (int64_t)Cin * xh * xw < (1 << 23),
+               "im2col_nchw: unsupported geometry (Cin*H*W must be < 2^23)");
+  const int64_t n = (int64_t)B * Ho * Wo * (ldcol / 8);
+  int nb = blocks_for(n, 256);
+  if (nb > 148 * 16) nb = 148 * 16;
+  const size_t tab = (size_t)K * sizeof(int);
+#define IM2COL_CASE(TI)                                                                                                     \
+  DISPATCH_T(dtype, (im2col_nchw_kernel<TI, T><<<nb, 256, tab, st>>>((const TI *)x, (T *)col, B, Cin, xh, xw, Ho, Wo, ksz, stride, \
+                                                                   pad, K, ldcol)))
   if (x_dtype == LEOD_U8) {
     IM2COL_CASE(uint8_t);
   } else if (x_dtype == LEOD_BF16) {
@@ -364,11 +428,12 @@ int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin
 
 int im2col_nhwc(int dtype, const void *x, void *col, int B, int Hi, int Wi, int Cin, int ksz, int stride, int pad, int ldcol,
                 cudaStream_t st) {
-  ProfScope ps(PK_PATCH, 0.0, ((double)B * (Hi / stride) * (Wi / stride) * ldcol + (double)B * Hi * Wi * Cin) * dtype_size(dtype), st);
+  ProfScope ps(PK_PATCH, 0.0, ((double)B * (Hi / stride) * (Wi / stride) * ldcol + (double)B * Hi * Wi * Cin) * dtype_size(dtype), st, B, Cin, 1);
   const int Ho = (Hi + 2 * pad - ksz) / stride + 1, Wo = (Wi + 2 * pad - ksz) / stride + 1;
   const int K = Cin * ksz * ksz;
-  const int64_t n = (int64_t)B * Ho * Wo * ldcol;
-  DISPATCH_T(dtype, (im2col_nhwc_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)x, (T *)col, B, Hi, Wi, Cin, Ho, Wo, ksz,
+  LEOD_REQUIRE(Cin % 8 == 0 && ldcol % 8 == 0, "im2col_nhwc: Cin=%d / pitch %d must be multiples of 8", Cin, ldcol);
+  const int64_t n = (int64_t)B * Ho * Wo * (ldcol / 8);
+  DISPATCH_T(dtype, (im2col_nhwc_kernel<T><<<std::min(blocks_for(n, 256), 148 * 16), 256, 0, st>>>((const T *)x, (T *)col, B, Hi, Wi, Cin, Ho, Wo, ksz,
                                                                               stride, pad, K, ldcol)));
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -376,10 +441,11 @@ int im2col_nhwc(int dtype, const void *x, void *col, int B, int Hi, int Wi, int 
 
 int col2im_nhwc(int dtype, const void *dcol, int ldcol, const void *dres, void *dx, int B, int Hi, int Wi, int Cin, int ksz,
                 int stride, int pad, cudaStream_t st) {
-  ProfScope ps(PK_PATCH, 0.0, ((double)B * (Hi / stride) * (Wi / stride) * ldcol + (double)B * Hi * Wi * Cin) * dtype_size(dtype), st);
+  ProfScope ps(PK_PATCH, 0.0, ((double)B * (Hi / stride) * (Wi / stride) * ldcol + (double)B * Hi * Wi * Cin) * dtype_size(dtype), st, B, Cin, 2);
   const int Ho = (Hi + 2 * pad - ksz) / stride + 1, Wo = (Wi + 2 * pad - ksz) / stride + 1;
-  const int64_t n = (int64_t)B * Hi * Wi * Cin;
-  DISPATCH_T(dtype, (col2im_nhwc_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)dcol, ldcol, (const T *)dres, (T *)dx, B,
+  LEOD_REQUIRE(Cin % 8 == 0 && ldcol % 8 == 0, "col2im_nhwc: Cin=%d / pitch %d must be multiples of 8", Cin, ldcol);
+  const int64_t n = (int64_t)B * Hi * Wi * (Cin / 8);
+  DISPATCH_T(dtype, (col2im_nhwc_kernel<T><<<std::min(blocks_for(n, 256), 148 * 16), 256, 0, st>>>((const T *)dcol, ldcol, (const T *)dres, (T *)dx, B,
                                                                               Hi, Wi, Cin, Ho, Wo, ksz, stride, pad)));
   LEOD_LAUNCH_CHECK();
   return 0;

@@ -73,13 +73,29 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// The wait names the destination registers as in/out operands so the compiler cannot schedule their
+// first use above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
         "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  tmem_ld_wait(r);
 }
 
 // shared-memory matrix descriptor, SWIZZLE_128B canonical layouts (cute/arch/mma_sm100_desc.hpp):
@@ -186,10 +202,19 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_nt_tc_kernel(const __grid_co
     tc_fence_after();
     const GemmNT &g = a.g;
     const bool row_ok = m < g.M;
-    for (int c = 0; c < a.BN; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
-      const int n = n0 + c;
+    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t rbuf[2][16];
+    tmem_ld16_async(trow, rbuf[0]);
+#pragma unroll 1
+    for (int c = 0; c < a.BN; c += 32) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+      const int cc = c + 16 * half;
+      if (cc >= a.BN) break;
+      tmem_ld_wait(rbuf[half]);
+      if (cc + 16 < a.BN) tmem_ld16_async(trow + (uint32_t)(cc + 16), rbuf[half ^ 1]);
+      const uint32_t (&r)[16] = rbuf[half];
+      const int n = n0 + cc;
       if (!row_ok || n >= g.N) continue;
       float v[16];
 #pragma unroll
@@ -246,6 +271,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_nt_tc_kernel(const __grid_co
           ((bf16 *)g.C)[(size_t)m * g.ldc + n + j] = __float2bfloat16_rn(x);
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -314,13 +340,151 @@ int make_map(CUtensorMap *out, const void *ptr, uint64_t inner, uint64_t outer, 
   return 0;
 }
 
-int pick_bn(int N) {
-  if (N <= 256) return (int)round_up(N, 16);
-  for (int bn = 256; bn >= 64; bn -= 16)
-    if (N % bn == 0) return bn;
-  return 128;
+// N tile: as wide as possible (A is read once per N tile) but (a) small-K tiles are latency bound, so
+// keep the TMEM allocation <= 128 columns there (4 CTAs per SM), and (b) small-M problems need enough
+// CTAs to cover the 148 SMs, so narrow the tile until the grid has >= ~120 CTAs.
+int pick_bn(int M, int N, int K) {
+  const int cap = K <= 128 ? 128 : 256;
+  const int tiles_m = ceil_div(M, TILE_M);
+  int best = 0;
+  for (int bn = cap; bn >= 32; bn -= 16) {
+    if (N % bn != 0 && !(N <= bn && bn == (int)round_up(N, 16))) continue;
+    if (best == 0) best = bn;
+    if (tiles_m * ceil_div(N, bn) >= 120) return bn;
+    best = bn;
+  }
+  if (best) return best;
+  return N <= cap ? (int)round_up(N, 16) : (cap == 128 ? 128 : 256);
 }
 
+
+// ------------------------------------------------------------------ TN (weight gradient) kernel
+// dW[n,k] += sum_m dY[m,n] X[m,k].  Both operands are MN-major for the MMA (the reduction index m is
+// the row index in memory), staged as 64-token x 64-element TMA boxes with 128B swizzle:
+//   canonical MN-major SW128 layout: 64 contiguous MN elements per token row (128 B), 8-row groups
+//   1024 B apart (SBO), successive 64-element MN blocks one box (8192 B) apart (LBO).
+struct TnArgs {
+  float *dW; int ldw;
+  int M, N, K;
+  int BKt;            // output columns per CTA (multiple of 64, <= 256)
+  int rows_per_split; // multiple of 64
+  int stages;
+  int tmem_cols;
+};
+
+constexpr int TN_BOX_BYTES = 64 * 64 * 2;  // 64 tokens x 64 elements
+
+__global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapY,
+                                                                 const __grid_constant__ CUtensorMap mapX, const TnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int nbx = a.BKt / 64;                              // X boxes per stage
+  const int stage_bytes = (2 + nbx) * TN_BOX_BYTES;
+  uint64_t *bars = (uint64_t *)(smem + (size_t)a.stages * stage_bytes);
+  uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages;
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * a.stages + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TILE_M, k0 = blockIdx.y * a.BKt;
+  const int m_begin = blockIdx.z * a.rows_per_split;
+  const int m_end = min(a.M, m_begin + a.rows_per_split);
+  const int nkb = (m_end - m_begin + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(tmem_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % a.stages;
+        const uint32_t ph = (kb / a.stages) & 1;
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[s]);
+        mbar_expect_tx(fb, stage_bytes);
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const int m = m_begin + kb * 64;
+        // rows beyond m_end belong to the next split: they are loaded (or zero-filled past M) but the
+        // split boundaries are multiples of 64, so only the global tail is ever partial
+        tma_load_2d(sa, &mapY, fb, n0, m);
+        tma_load_2d(sa + TN_BOX_BYTES, &mapY, fb, n0 + 64, m);
+        for (int j = 0; j < nbx; ++j) tma_load_2d(sa + (2 + j) * TN_BOX_BYTES, &mapX, fb, k0 + 64 * j, m);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TILE_M, a.BKt, 1, 1);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % a.stages;
+        const uint32_t ph = (kb / a.stages) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + 2 * TN_BOX_BYTES;
+        const uint64_t adesc = make_desc(sa, TN_BOX_BYTES, 1024), bdesc = make_desc(sb, TN_BOX_BYTES, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // 16 tokens per MMA = 16 rows of 128 B = 2048 B (>>4: +128)
+          tc_mma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (kb | k) != 0);
+        }
+        tc_commit(smem_u32(&empty_bar[s]));
+      }
+      tc_commit(smem_u32(tmem_full));
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int n = n0 + quarter * 32 + lane;
+    mbar_wait(smem_u32(tmem_full), 0);
+    tc_fence_after();
+    for (int c = 0; c < a.BKt; c += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
+      if (n >= a.N) continue;
+      float *dst = a.dW + (size_t)n * a.ldw + k0 + c;
+      if (gridDim.z == 1 && k0 + c + 16 <= a.K && (((uintptr_t)dst) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 v = reinterpret_cast<float4 *>(dst)[q];
+          v.x += __uint_as_float(r[4 * q]); v.y += __uint_as_float(r[4 * q + 1]);
+          v.z += __uint_as_float(r[4 * q + 2]); v.w += __uint_as_float(r[4 * q + 3]);
+          reinterpret_cast<float4 *>(dst)[q] = v;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (k0 + c + j < a.K) atomicAdd(dst + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+  }
+}
+
+// column sums of a bf16 matrix into fp32 (bias gradients)
+__global__ void colsum_bf16_kernel(const bf16 *__restrict__ Y, int ldy, float *__restrict__ out, int M, int N, int rows_per_block) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc = 0.f;
+  for (int m = m0; m < m1; ++m) acc += __bfloat162float(Y[(size_t)m * ldy + n]);
+  atomicAdd(&out[n], acc);
+}
 }  // namespace
 
 int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
@@ -331,7 +495,7 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   LEOD_REQUIRE((((uintptr_t)g.C) & 15) == 0, "gemm_nt_tc: C not 16-byte aligned");
   NtArgs a;
   a.g = g;
-  a.BN = pick_bn(g.N);
+  a.BN = pick_bn(g.M, g.N, g.K);
   const int K1 = g.A2 ? g.K1 : g.K, K2 = g.K - K1;
   LEOD_REQUIRE(K1 > 0 && K2 >= 0 && (K2 == 0 || K1 % 8 == 0), "gemm_nt_tc: bad K split %d/%d", K1, g.K);
   a.nkb1 = ceil_div(K1, TILE_K);
@@ -364,7 +528,45 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
 
 int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N, int K,
                cudaStream_t st) {
-  // weight-gradient GEMM: the tcgen05 MN-major version is staged behind this entry point; until it
-  // is enabled the bf16 operands go through the SIMT kernel (fp32 accumulate, same results).
-  return gemm_tn_simt(LEOD_BF16, dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, st);
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (ldy % 8 != 0 || ldx % 8 != 0 || (((uintptr_t)dY | (uintptr_t)X) & 15) != 0) {
+    // TMA needs 16-byte aligned rows: odd shapes (never produced by the backbone) take the SIMT kernel
+    return gemm_tn_simt(LEOD_BF16, dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, st);
+  }
+  TnArgs a;
+  a.dW = dW; a.ldw = ldw; a.M = M; a.N = N; a.K = K;
+  a.BKt = K >= 256 ? 256 : (int)round_up(K, 64);
+  const int tn = ceil_div(N, TILE_M), tk = ceil_div(K, a.BKt);
+  // each split ends in an atomic epilogue over the whole output tile, so splits are only worth it when
+  // they still stream a few thousand rows each; small-M problems run unsplit (plain read-modify-write)
+  int splits = ceil_div(148, tn * tk);
+  const int max_splits = M <= 4096 ? 1 : ceil_div(M, 2048);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  a.rows_per_split = (int)round_up(ceil_div(M, splits), 64);
+  splits = ceil_div(M, a.rows_per_split);
+  const int nkb = a.rows_per_split / 64;
+  a.stages = nkb < 4 ? nkb : 4;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.BKt) a.tmem_cols *= 2;
+  CUtensorMap mY, mX;
+  LEOD_TRY(make_map(&mY, dY, N, M, ldy, 64, 64));
+  LEOD_TRY(make_map(&mX, X, K, M, ldx, 64, 64));
+  const int stage_bytes = (2 + a.BKt / 64) * TN_BOX_BYTES;
+  const size_t smem = (size_t)a.stages * stage_bytes + 1024 + (2 * a.stages + 2) * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LEOD_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr_set = true;
+  }
+  dim3 grid(tn, tk, splits);
+  gemm_tn_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(mY, mX, a);
+  LEOD_LAUNCH_CHECK();
+  if (dbias) {
+    const int rpb = (int)round_up(ceil_div(M, 148 * 2), 32);
+    dim3 g2(ceil_div(N, 128), ceil_div(M, rpb));
+    colsum_bf16_kernel<<<g2, 128, 0, st>>>((const bf16 *)dY, ldy, dbias, M, N, rpb);
+    LEOD_LAUNCH_CHECK();
+  }
+  return 0;
 }

@@ -171,6 +171,70 @@ def test_attention_fwd_bwd(dtype, window, B, H, W, C, dh, part):
     assert rel_err(dqkv.float(), q32.grad) < tol
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('M,C', [(1000, 48), (4099, 96), (640, 384), (77, 512), (300, 16)])
+def test_layernorm_fwd_bwd(dtype, M, C):
+    L = _lib()
+    g = torch.Generator(device='cuda').manual_seed(M + C)
+    x = (torch.randn(M, C, device='cuda', generator=g) * 2 + 0.5).to(dtype)
+    dy = torch.randn(M, C, device='cuda', generator=g).to(dtype)
+    dres = torch.randn(M, C, device='cuda', generator=g).to(dtype)
+    w = torch.rand(C, device='cuda', generator=g) + 0.5
+    b = torch.randn(C, device='cuda', generator=g)
+    y = torch.empty_like(x)
+    dx = torch.empty_like(x)
+    dw = torch.full((C,), 0.25, device='cuda')
+    db = torch.full((C,), -0.5, device='cuda')
+    dt = BF16 if dtype == torch.bfloat16 else F32
+    L.check(L.lib().leod_layernorm_fwd(dt, L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), M, C, 1e-5, L.stream_ptr()))
+    L.check(L.lib().leod_layernorm_bwd(dt, L.ptr(x), L.ptr(w), L.ptr(dy), L.ptr(dres), L.ptr(dx), L.ptr(dw), L.ptr(db), M, C, 1e-5,
+                                       L.stream_ptr()))
+    torch.cuda.synchronize()
+    x32 = x.float().requires_grad_(True)
+    w32 = w.clone().requires_grad_(True)
+    b32 = b.clone().requires_grad_(True)
+    ref = F.layer_norm(x32, (C,), w32, b32, 1e-5)
+    ref.backward(dy.float())
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert rel_err(y.float(), ref.detach()) < tol
+    assert rel_err(dx.float(), x32.grad + dres.float()) < tol
+    assert rel_err(dw, 0.25 + w32.grad) < 1e-3
+    assert rel_err(db, -0.5 + b32.grad) < 1e-3
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('M,C,with_prev', [(1000, 48, True), (640, 384, True), (333, 96, False)])
+def test_lstm_gates_fwd_bwd(dtype, M, C, with_prev):
+    L = _lib()
+    g = torch.Generator(device='cuda').manual_seed(M + C)
+    pre = torch.randn(M, 4 * C, device='cuda', generator=g).to(dtype)
+    c0 = torch.randn(M, C, device='cuda', generator=g).to(dtype) if with_prev else None
+    dh = torch.randn(M, C, device='cuda', generator=g).to(dtype)
+    dh2 = torch.randn(M, C, device='cuda', generator=g).to(dtype)
+    dc = torch.randn(M, C, device='cuda', generator=g).to(dtype)
+    gates = pre.clone()
+    h1, c1 = torch.empty(M, C, device='cuda', dtype=dtype), torch.empty(M, C, device='cuda', dtype=dtype)
+    dgates = torch.empty(M, 4 * C, device='cuda', dtype=dtype)
+    dc0 = torch.empty(M, C, device='cuda', dtype=dtype)
+    dt = BF16 if dtype == torch.bfloat16 else F32
+    L.check(L.lib().leod_lstm_gates_fwd(dt, L.ptr(gates), L.ptr(c0), L.ptr(h1), L.ptr(c1), M, C, L.stream_ptr()))
+    L.check(L.lib().leod_lstm_gates_bwd(dt, L.ptr(gates), L.ptr(c0), L.ptr(c1), L.ptr(dh), L.ptr(dh2), L.ptr(dc), L.ptr(dgates),
+                                        L.ptr(dc0), M, C, L.stream_ptr()))
+    torch.cuda.synchronize()
+    p32 = pre.float().requires_grad_(True)
+    c32 = (c0.float() if with_prev else torch.zeros(M, C, device='cuda')).requires_grad_(True)
+    f, i, o = (torch.sigmoid(p32[:, k * C:(k + 1) * C]) for k in range(3))
+    gg = torch.tanh(p32[:, 3 * C:])
+    cr = f * c32 + i * gg
+    hr = o * torch.tanh(cr)
+    (hr * (dh.float() + dh2.float())).sum().add((cr * dc.float()).sum()).backward()
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert rel_err(h1.float(), hr.detach()) < tol
+    assert rel_err(c1.float(), cr.detach()) < tol
+    assert rel_err(dgates.float(), p32.grad) < tol
+    assert rel_err(dc0.float(), c32.grad) < tol
+
+
 def test_postprocess_matches_oracle_and_fixture():
     from oracle import postprocess as opp
     from leod_b200.models.detection.yolox.utils.boxes import postprocess, postprocess_packed
