@@ -60,7 +60,7 @@ def synth_batch(seed, device=None, pin=False):
 
 def make_batch(ev_dev, labels, first):
     from leod_b200.data.utils.types import DataType
-    return {'worker_id': 0, 'data': {DataType.EV_REPR: [ev_dev[t] for t in range(ev_dev.shape[0])],
+    return {'worker_id': 0, 'data': {DataType.EV_REPR: ev_dev,
                                      DataType.OBJLABELS_SEQ: labels, DataType.IS_FIRST_SAMPLE: first}}
 
 

@@ -97,6 +97,24 @@ int leod_backbone_step_bwd(leod_backbone_t *h, const void *x, int x_dtype, int x
                            const void *const h_prev[4], const void *const c_prev[4], const void *const h_out[4],
                            const void *const c_out[4], const void *save, const void *const dh_out[4], const void *const dc_out[4],
                            void *const dh_prev[4], void *const dc_prev[4], void *stream);
+/* A whole BPTT window (L timesteps) in one call — the fast path.  Stage 1 up to its LSTM is independent of the
+ * recurrent state and runs batched over all L*B frames; weight gradients are computed by one GEMM per layer over
+ * all timesteps.  Activations live in a library-owned arena (leod_backbone_seq_arena_bytes), so a forward must be
+ * followed by at most one backward with the same (B, L) before the next forward.
+ *  x      : device [L, B, in_channels, x_h, x_w], dtype x_dtype
+ *  h0/c0  : initial state per stage (NHWC, storage dtype) or NULL
+ *  h_all  : out, per stage [L, B, h, w, C] hidden states of every timestep (= the features)
+ *  c_last : out, per stage [B, h, w, C] cell state after the last timestep
+ * Backward: dh_all[s] ([L,B,h,w,C] or NULL) and dc_last[s] ([B,h,w,C] or NULL) are the output gradients;
+ * dh0/dc0 (NULL entries allowed) receive the gradients w.r.t. the initial state. */
+int64_t leod_backbone_seq_arena_bytes(const leod_backbone_t *h, int B, int L);
+int leod_backbone_seq_fwd(leod_backbone_t *h, const void *x, int x_dtype, int x_h, int x_w, int B, int L,
+                          const void *const h0[4], const void *const c0[4], void *const h_all[4], void *const c_last[4],
+                          void *stream);
+int leod_backbone_seq_bwd(leod_backbone_t *h, const void *x, int x_dtype, int x_h, int x_w, int B, int L,
+                          const void *const h0[4], const void *const c0[4], const void *const h_all[4],
+                          const void *const dh_all[4], const void *const dc_last[4], void *const dh0[4], void *const dc0[4],
+                          void *stream);
 /* Fold the internal scratch into the bound gradient buffer; call once after the last step_bwd of a
  * backward pass. */
 int leod_backbone_grads_finalize(leod_backbone_t *h, void *stream);

@@ -48,6 +48,9 @@ def _declare(lib):
         'leod_backbone_step_fwd': (I, [VP, VP, I, I, I, I, _VP4, _VP4, _VP4, _VP4, VP, VP]),
         'leod_backbone_step_bwd': (I, [VP, VP, I, I, I, I, _VP4, _VP4, _VP4, _VP4, VP, _VP4, _VP4, _VP4, _VP4, VP]),
         'leod_backbone_grads_finalize': (I, [VP, VP]),
+        'leod_backbone_seq_arena_bytes': (c_int64, [VP, I, I]),
+        'leod_backbone_seq_fwd': (I, [VP, VP, I, I, I, I, I, _VP4, _VP4, _VP4, _VP4, VP]),
+        'leod_backbone_seq_bwd': (I, [VP, VP, I, I, I, I, I, _VP4, _VP4, _VP4, _VP4, _VP4, _VP4, _VP4, VP]),
         'leod_gemm_nt': (I, [I, I, VP, I, VP, I, I, VP, I, VP, I, I, I, I, VP, I, VP, I, VP, I, VP]),
         'leod_gemm_tn': (I, [I, I, VP, I, VP, I, VP, I, VP, I, I, I, VP]),
         'leod_attention_fwd': (I, [I, VP, VP, I, I, I, I, I, I, I, I, VP]),
@@ -73,7 +76,8 @@ EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 
                     'leod_backbone_destroy',
                     'leod_backbone_param_info', 'leod_backbone_param_count', 'leod_backbone_bind', 'leod_backbone_prepare',
                     'leod_backbone_save_bytes', 'leod_backbone_reserve', 'leod_backbone_set_gemm_impl',
-                    'leod_backbone_step_fwd', 'leod_backbone_step_bwd', 'leod_backbone_grads_finalize', 'leod_gemm_nt',
+                    'leod_backbone_step_fwd', 'leod_backbone_step_bwd', 'leod_backbone_grads_finalize', 'leod_backbone_seq_arena_bytes',
+                    'leod_backbone_seq_fwd', 'leod_backbone_seq_bwd', 'leod_gemm_nt',
                     'leod_gemm_tn', 'leod_attention_fwd', 'leod_attention_bwd', 'leod_layernorm_fwd', 'leod_layernorm_bwd',
                     'leod_lstm_gates_fwd', 'leod_lstm_gates_bwd', 'leod_postprocess', 'leod_pred2label',
                     'leod_voxel_bin', 'leod_adamw_ema']

@@ -42,12 +42,18 @@ struct StageW {
 struct StageD {
   int Cin, C, ksz, stride, pad, Hi, Wi, Ho, Wo, K, Kp;
 };
-struct SaveOff {  // element offsets (operand dtype) inside one step's save buffer, per stage
-  int64_t y0, x0;
-  struct {
-    int64_t xn1, qkv, att, x1, xn2, u, a, x2;
-  } blk[2];
-  int64_t gates;
+// Activations kept for the backward pass (SB) and the output-gradient tensors the weight-gradient GEMMs read
+// (GB).  Every entry is a matrix [rows, cols] in the operand dtype; in sequence mode rows = L * M_stage with the
+// timestep as the slowest index, so one weight-gradient GEMM covers the whole BPTT window.
+struct SB {
+  void *y0, *x0, *xn1, *qkv[2], *att[2], *x1[2], *xn2[2], *u[2], *a[2], *x2[2], *gates;
+};
+struct GB {
+  void *dgates, *dy2[2], *du[2], *dy1[2], *dqkv[2], *dy0;
+};
+struct StageLayout {  // element offsets of one stage inside an arena holding `slots` timesteps
+  int64_t y0, x0, xn1, qkv[2], att[2], x1[2], xn2[2], u[2], a[2], x2[2], gates, c_all;
+  int64_t dgates, dy2[2], du[2], dy1[2], dqkv[2], dy0;
 };
 
 }  // namespace
@@ -61,10 +67,15 @@ struct leod_backbone {
   int64_t n_params = 0;
   float *params = nullptr, *grads = nullptr;
   std::vector<void *> owned;  // cudaMalloc'ed
-  // workspace
+  // workspace (sized for ws_rows0 = stage-0 rows of the largest batch of images processed at once)
+  int64_t ws_imgs = 0;
   int ws_B = 0;
-  void *ws_col = nullptr, *ws_big4 = nullptr, *ws_qkv = nullptr, *ws_a = nullptr, *ws_b = nullptr, *ws_c = nullptr,
-       *ws_hint = nullptr, *ws_save = nullptr;
+  void *ws_col = nullptr, *ws_dxn = nullptr, *ws_dx0 = nullptr, *ws_hint = nullptr, *ws_save = nullptr, *ws_stash = nullptr;
+  int64_t ws_col_elems = 0;
+  void *ws_dhc[4] = {nullptr, nullptr, nullptr, nullptr}, *ws_dcc[4] = {nullptr, nullptr, nullptr, nullptr};
+  // sequence arena
+  int seq_B = 0, seq_L = 0;
+  void *seq_arena = nullptr;
   size_t esz() const { return cfg.dtype == LEOD_BF16 ? 2 : 4; }
   int gemm_impl = 0;  // 0 SIMT, 1 tensor core (bf16 only)
 };
@@ -88,62 +99,6 @@ int dev_alloc(leod_backbone *h, void **p, size_t bytes, bool zero = true) {
   LEOD_CUDA(cudaMalloc(p, bytes ? bytes : 16));
   if (zero) LEOD_CUDA(cudaMemset(*p, 0, bytes ? bytes : 16));
   h->owned.push_back(*p);
-  return 0;
-}
-
-void compute_save_layout(const leod_backbone *h, int B, SaveOff off[4], int64_t *total_elems) {
-  int64_t cur = 0;
-  auto take = [&](int64_t n) {
-    int64_t o = cur;
-    cur += round_up(n, 128);
-    return o;
-  };
-  for (int s = 0; s < 4; ++s) {
-    const StageD &d = h->d[s];
-    const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
-    off[s].y0 = take(M * C);
-    off[s].x0 = take(M * C);
-    for (int b = 0; b < 2; ++b) {
-      off[s].blk[b].xn1 = (b == 1) ? take(M * C) : -1;
-      off[s].blk[b].qkv = take(M * 3 * C);
-      off[s].blk[b].att = take(M * C);
-      off[s].blk[b].x1 = take(M * C);
-      off[s].blk[b].xn2 = take(M * C);
-      off[s].blk[b].u = take(M * h->cfg.mlp_ratio * C);
-      off[s].blk[b].a = take(M * h->cfg.mlp_ratio * C);
-      off[s].blk[b].x2 = take(M * C);
-    }
-    off[s].gates = take(M * 4 * C);
-  }
-  *total_elems = cur;
-}
-
-int ensure_workspace(leod_backbone *h, int B) {
-  if (B <= h->ws_B) return 0;
-  for (void **p : {&h->ws_col, &h->ws_big4, &h->ws_qkv, &h->ws_a, &h->ws_b, &h->ws_c, &h->ws_hint, &h->ws_save}) {
-    if (*p) cudaFree(*p);
-    *p = nullptr;
-  }
-  const size_t e = h->esz();
-  int64_t col = 0, mc = 0;
-  for (int s = 0; s < 4; ++s) {
-    const StageD &d = h->d[s];
-    const int64_t M = (int64_t)B * d.Ho * d.Wo;
-    col = std::max<int64_t>(col, M * d.Kp);
-    mc = std::max<int64_t>(mc, M * d.C);
-  }
-  SaveOff off[4];
-  int64_t save_elems;
-  compute_save_layout(h, B, off, &save_elems);
-  LEOD_CUDA(cudaMalloc(&h->ws_col, col * e));
-  LEOD_CUDA(cudaMalloc(&h->ws_big4, mc * std::max(4, h->cfg.mlp_ratio) * e));
-  LEOD_CUDA(cudaMalloc(&h->ws_qkv, mc * 3 * e));
-  LEOD_CUDA(cudaMalloc(&h->ws_a, mc * e));
-  LEOD_CUDA(cudaMalloc(&h->ws_b, mc * e));
-  LEOD_CUDA(cudaMalloc(&h->ws_c, mc * e));
-  LEOD_CUDA(cudaMalloc(&h->ws_hint, mc * e));
-  LEOD_CUDA(cudaMalloc(&h->ws_save, save_elems * e));
-  h->ws_B = B;
   return 0;
 }
 
@@ -181,6 +136,286 @@ __global__ void conv_grad_unpermute_kernel(float *__restrict__ G, float *__restr
   const int cin = k % Cin, kx = (k / Cin) % ksz, ky = k / (Cin * ksz);
   dW[(((size_t)n * Cin + cin) * ksz + ky) * ksz + kx] += G[idx];
   G[idx] = 0.f;
+}
+
+
+// ------------------------------------------------------------------ arena layout
+// slots = number of timesteps the arena holds; with_stash adds the gradient-side tensors; with_c adds c_all.
+void compute_layout(const leod_backbone *h, int B, int slots, bool with_stash, bool with_c, StageLayout lay[4], int64_t *total) {
+  int64_t cur = 0;
+  auto take = [&](int64_t n) {
+    const int64_t o = cur;
+    cur += round_up(n, 128);
+    return o;
+  };
+  const int64_t R = h->cfg.mlp_ratio;
+  for (int s = 0; s < 4; ++s) {
+    const StageD &d = h->d[s];
+    const int64_t M = (int64_t)B * d.Ho * d.Wo * slots, C = d.C;
+    StageLayout &l = lay[s];
+    l.y0 = take(M * C);
+    l.x0 = take(M * C);
+    l.xn1 = take(M * C);
+    for (int b = 0; b < 2; ++b) {
+      l.qkv[b] = take(M * 3 * C);
+      l.att[b] = take(M * C);
+      l.x1[b] = take(M * C);
+      l.xn2[b] = take(M * C);
+      l.u[b] = take(M * R * C);
+      l.a[b] = take(M * R * C);
+      l.x2[b] = take(M * C);
+    }
+    l.gates = take(M * 4 * C);
+    l.c_all = with_c ? take(M * C) : -1;
+    if (with_stash) {
+      l.dgates = take(M * 4 * C);
+      for (int b = 0; b < 2; ++b) {
+        l.dy2[b] = take(M * C);
+        l.du[b] = take(M * R * C);
+        l.dy1[b] = take(M * C);
+        l.dqkv[b] = take(M * 3 * C);
+      }
+      l.dy0 = take(M * C);
+    }
+  }
+  *total = cur;
+}
+
+// saved-activation pointers of stage s starting at timestep slot t
+SB sb_at(const leod_backbone *h, const void *base, const StageLayout &l, int s, int B, int t) {
+  const StageD &d = h->d[s];
+  const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C, R = h->cfg.mlp_ratio, e = (int64_t)h->esz();
+  auto at = [&](int64_t off, int64_t cols) { return (void *)((char *)base + (off + t * M * cols) * e); };
+  SB b;
+  b.y0 = at(l.y0, C); b.x0 = at(l.x0, C); b.xn1 = at(l.xn1, C);
+  for (int k = 0; k < 2; ++k) {
+    b.qkv[k] = at(l.qkv[k], 3 * C); b.att[k] = at(l.att[k], C); b.x1[k] = at(l.x1[k], C); b.xn2[k] = at(l.xn2[k], C);
+    b.u[k] = at(l.u[k], R * C); b.a[k] = at(l.a[k], R * C); b.x2[k] = at(l.x2[k], C);
+  }
+  b.gates = at(l.gates, 4 * C);
+  return b;
+}
+GB gb_at(const leod_backbone *h, const void *base, const StageLayout &l, int s, int B, int t) {
+  const StageD &d = h->d[s];
+  const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C, R = h->cfg.mlp_ratio, e = (int64_t)h->esz();
+  auto at = [&](int64_t off, int64_t cols) { return (void *)((char *)base + (off + t * M * cols) * e); };
+  GB g;
+  g.dgates = at(l.dgates, 4 * C);
+  for (int k = 0; k < 2; ++k) {
+    g.dy2[k] = at(l.dy2[k], C); g.du[k] = at(l.du[k], R * C); g.dy1[k] = at(l.dy1[k], C); g.dqkv[k] = at(l.dqkv[k], 3 * C);
+  }
+  g.dy0 = at(l.dy0, C);
+  return g;
+}
+
+void free_workspace(leod_backbone *h) {
+  for (void **p : {&h->ws_col, &h->ws_dxn, &h->ws_dx0, &h->ws_hint, &h->ws_save, &h->ws_stash}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  for (int s = 0; s < 4; ++s) {
+    if (h->ws_dhc[s]) cudaFree(h->ws_dhc[s]);
+    if (h->ws_dcc[s]) cudaFree(h->ws_dcc[s]);
+    h->ws_dhc[s] = h->ws_dcc[s] = nullptr;
+  }
+  h->ws_imgs = 0;
+  h->ws_B = 0;
+}
+
+// Workspace for processing up to `imgs` images of any stage in one go (imgs = B per-step, L*B batched).
+int ensure_workspace(leod_backbone *h, int64_t imgs, int B) {
+  if (imgs <= h->ws_imgs && B <= h->ws_B) return 0;
+  imgs = std::max<int64_t>(imgs, h->ws_imgs);
+  B = std::max(B, h->ws_B);
+  free_workspace(h);
+  const int64_t e = (int64_t)h->esz();
+  int64_t mc = 0, col = 0;
+  for (int s = 0; s < 4; ++s) {
+    const StageD &d = h->d[s];
+    mc = std::max<int64_t>(mc, imgs * d.Ho * d.Wo * d.C);
+    // patch matrix: whole-batch for a single step, capped (chunked) for long batched runs
+    col = std::max<int64_t>(col, std::min<int64_t>(imgs, std::max<int64_t>(B, 32)) * d.Ho * d.Wo * d.Kp);
+  }
+  h->ws_col_elems = col;
+  LEOD_CUDA(cudaMalloc(&h->ws_col, col * e));
+  LEOD_CUDA(cudaMalloc(&h->ws_dxn, mc * e));
+  LEOD_CUDA(cudaMalloc(&h->ws_dx0, mc * e));
+  LEOD_CUDA(cudaMalloc(&h->ws_hint, mc * e));
+  StageLayout lay[4];
+  int64_t n;
+  compute_layout(h, B, 1, true, false, lay, &n);   // one-slot save (inference) + stash (per-step backward)
+  LEOD_CUDA(cudaMalloc(&h->ws_save, n * e));
+  LEOD_CUDA(cudaMalloc(&h->ws_stash, n * e));
+  for (int s = 0; s < 4; ++s) {
+    const StageD &d = h->d[s];
+    const int64_t m = (int64_t)B * d.Ho * d.Wo * d.C;
+    LEOD_CUDA(cudaMalloc(&h->ws_dhc[s], m * e));
+    LEOD_CUDA(cudaMalloc(&h->ws_dcc[s], m * e));
+  }
+  h->ws_imgs = imgs;
+  h->ws_B = B;
+  return 0;
+}
+
+// ------------------------------------------------------------------ stage pieces (shared by step and sequence mode)
+// conv downsample + LN + window block + grid block for `nimg` images.  `in`: stage input (x for stage 0, else the
+// previous stage's hidden state, channels-last).
+int front_fwd(leod_backbone *h, int s, int64_t nimg, const void *in, int x_dtype, int x_h, int x_w, const SB &b, cudaStream_t st) {
+  const StageD &d = h->d[s];
+  const StageP &p = h->p[s];
+  const StageW &w = h->w[s];
+  const int dt = h->cfg.dtype, C = d.C, R = h->cfg.mlp_ratio;
+  const float eps = h->cfg.ln_eps;
+  const float *P = h->params;
+  const int64_t rows_per_img = (int64_t)d.Ho * d.Wo, e = (int64_t)h->esz();
+  const int64_t M64 = nimg * rows_per_img;
+  LEOD_REQUIRE(M64 * std::max(4 * C, d.Kp) < (1LL << 31), "stage %d: %lld rows exceed the 32-bit indexing of the kernels", s, (long long)M64);
+  const int M = (int)M64;
+  const int64_t chunk_imgs = std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
+  for (int64_t i0 = 0; i0 < nimg; i0 += chunk_imgs) {
+    const int n = (int)std::min<int64_t>(chunk_imgs, nimg - i0);
+    if (s == 0) {
+      const char *xin = (const char *)in + i0 * d.Cin * x_h * x_w * (int64_t)dtype_size(x_dtype);
+      LEOD_TRY(im2col_nchw(x_dtype, dt, xin, h->ws_col, n, d.Cin, x_h, x_w, d.Hi, d.Wi, d.ksz, d.stride, d.pad, d.Kp, st));
+    } else {
+      const char *xin = (const char *)in + i0 * d.Hi * d.Wi * d.Cin * e;
+      LEOD_TRY(im2col_nhwc(dt, xin, h->ws_col, n, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, d.Kp, st));
+    }
+    LEOD_TRY(gemm_nt(h, mk(h->ws_col, d.Kp, w.Wconv, d.Kp, (char *)b.y0 + i0 * rows_per_img * C * e, C, (int)(n * rows_per_img), C, d.Kp), st));
+  }
+  LEOD_TRY(layernorm_fwd(dt, b.y0, P + p.lnw, P + p.lnb, b.x0, M, C, 1e-5f, st));
+  const void *xin = b.x0;
+  const int nimg_i = (int)nimg;
+  for (int k = 0; k < 2; ++k) {
+    const BlockP &q = p.blk[k];
+    const BlockW &bw = w.blk[k];
+    const void *ain = xin;
+    if (k == 1) {
+      LEOD_TRY(layernorm_fwd(dt, xin, P + q.n1w, P + q.n1b, b.xn1, M, C, eps, st));
+      ain = b.xn1;
+    }
+    LEOD_TRY(gemm_nt(h, mk(ain, C, bw.Wqkv, C, b.qkv[k], 3 * C, M, 3 * C, C, P + q.qkvb), st));
+    LEOD_TRY(attention_fwd(dt, b.qkv[k], b.att[k], nimg_i, d.Ho, d.Wo, C, h->cfg.dim_head, h->cfg.part_h, h->cfg.part_w, k == 0, st));
+    LEOD_TRY(gemm_nt(h, mk(b.att[k], C, bw.Wproj, C, b.x1[k], C, M, C, C, bw.bproj, EPI_RESID, xin, C), st));
+    LEOD_TRY(layernorm_fwd(dt, b.x1[k], P + q.n2w, P + q.n2b, b.xn2[k], M, C, eps, st));
+    LEOD_TRY(gemm_nt(h, mk(b.xn2[k], C, bw.W1, C, b.a[k], R * C, M, R * C, C, P + q.fc1b, EPI_GELU, nullptr, 0, b.u[k], R * C), st));
+    LEOD_TRY(gemm_nt(h, mk(b.a[k], R * C, bw.W2, R * C, b.x2[k], C, M, C, R * C, bw.b2, EPI_RESID, b.x1[k], C), st));
+    xin = b.x2[k];
+  }
+  return 0;
+}
+
+int lstm_fwd(leod_backbone *h, int s, int M, const void *x2, const void *h_prev, const void *c_prev, void *gates, void *h_out,
+             void *c_out, cudaStream_t st) {
+  const StageD &d = h->d[s];
+  const int C = d.C;
+  GemmNT g = mk(x2, C, h->w[s].Wl, 2 * C, gates, 4 * C, M, 4 * C, C, h->params + h->p[s].lstmb);
+  if (h_prev) {
+    g.A2 = h_prev; g.lda2 = C; g.K = 2 * C; g.K1 = C;
+  }
+  LEOD_TRY(gemm_nt(h, g, st));
+  return lstm_pointwise_fwd(h->cfg.dtype, gates, c_prev, h_out, c_out, M, C, st);
+}
+
+// gate math backward + the two input-gradient GEMMs.  dx2 -> g.dy2[1]; dh_prev written when non-null.
+int lstm_bwd(leod_backbone *h, int s, int M, const void *gates, const void *c_prev, const void *c_out, const void *dh_a,
+             const void *dh_b, const void *dh_c, const void *dc, const GB &g, void *dc_prev, void *dh_prev, cudaStream_t st) {
+  const StageD &d = h->d[s];
+  const int C = d.C;
+  const StageW &w = h->w[s];
+  LEOD_TRY(lstm_pointwise_bwd(h->cfg.dtype, gates, c_prev, c_out, dh_a, dh_b, dc, g.dgates, dc_prev, M, C, st, dh_c));
+  LEOD_TRY(gemm_nt(h, mk(g.dgates, 4 * C, w.WlT, 4 * C, g.dy2[1], C, M, C, 4 * C), st));
+  if (dh_prev) LEOD_TRY(gemm_nt(h, mk(g.dgates, 4 * C, eoff(h, w.WlT, (int64_t)C * 4 * C), 4 * C, dh_prev, C, M, C, 4 * C), st));
+  return 0;
+}
+
+// input gradients of the two blocks and the downsample; output-gradient tensors land in g for the deferred
+// weight-gradient GEMMs.  hint_out (stage > 0): gradient w.r.t. the stage input (previous stage's h), channels-last.
+int front_bwd(leod_backbone *h, int s, int64_t nimg, const SB &b, const GB &g, void *hint_out, cudaStream_t st) {
+  const StageD &d = h->d[s];
+  const StageP &p = h->p[s];
+  const StageW &w = h->w[s];
+  const int dt = h->cfg.dtype, C = d.C, R = h->cfg.mlp_ratio;
+  const float eps = h->cfg.ln_eps;
+  const float *P = h->params;
+  float *G = h->grads;
+  const int64_t rows_per_img = (int64_t)d.Ho * d.Wo, e = (int64_t)h->esz();
+  const int M = (int)(nimg * rows_per_img);
+  void *dxn = h->ws_dxn;
+  for (int k = 1; k >= 0; --k) {
+    const BlockP &q = p.blk[k];
+    const BlockW &bw = w.blk[k];
+    const void *xin = (k == 1) ? b.x2[0] : b.x0;
+    // MLP: x2 = x1 + W2'(gelu(W1 LN2(x1) + b1)) + b2'
+    LEOD_TRY(gemm_nt(h, mk(g.dy2[k], C, bw.W2T, C, g.du[k], R * C, M, R * C, C, nullptr, EPI_GELU_BWD, nullptr, 0, b.u[k], R * C), st));
+    LEOD_TRY(gemm_nt(h, mk(g.du[k], R * C, bw.W1T, R * C, dxn, C, M, C, R * C), st));
+    LEOD_TRY(layernorm_bwd(dt, b.x1[k], P + q.n2w, dxn, g.dy2[k], g.dy1[k], G + q.n2w, G + q.n2b, M, C, eps, st));
+    // attention: x1 = xin + Wp'(attn(Wqkv LN1(xin))) + bp'
+    LEOD_TRY(gemm_nt(h, mk(g.dy1[k], C, bw.WprojT, C, dxn, C, M, C, C), st));
+    LEOD_TRY(attention_bwd(dt, b.qkv[k], dxn, g.dqkv[k], (int)nimg, d.Ho, d.Wo, C, h->cfg.dim_head, h->cfg.part_h, h->cfg.part_w, k == 0, st));
+    if (k == 1) {
+      LEOD_TRY(gemm_nt(h, mk(g.dqkv[k], 3 * C, bw.WqkvT, 3 * C, dxn, C, M, C, 3 * C), st));
+      LEOD_TRY(layernorm_bwd(dt, xin, P + q.n1w, dxn, g.dy1[k], g.dy2[0], G + q.n1w, G + q.n1b, M, C, eps, st));
+    } else {
+      LEOD_TRY(gemm_nt(h, mk(g.dqkv[k], 3 * C, bw.WqkvT, 3 * C, h->ws_dx0, C, M, C, 3 * C, nullptr, EPI_RESID, g.dy1[k], C), st));
+    }
+  }
+  LEOD_TRY(layernorm_bwd(dt, b.y0, P + p.lnw, h->ws_dx0, nullptr, g.dy0, G + p.lnw, G + p.lnb, M, C, 1e-5f, st));
+  if (s > 0 && hint_out) {
+    const int64_t chunk_imgs = std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
+    for (int64_t i0 = 0; i0 < nimg; i0 += chunk_imgs) {
+      const int n = (int)std::min<int64_t>(chunk_imgs, nimg - i0);
+      LEOD_TRY(gemm_nt(h, mk((char *)g.dy0 + i0 * rows_per_img * C * e, C, w.WconvT, C, h->ws_col, d.Kp, (int)(n * rows_per_img), d.K, C), st));
+      LEOD_TRY(col2im_nhwc(dt, h->ws_col, d.Kp, nullptr, (char *)hint_out + i0 * d.Hi * d.Wi * d.Cin * e, n, d.Hi, d.Wi, d.Cin, d.ksz,
+                           d.stride, d.pad, st));
+    }
+  }
+  return 0;
+}
+
+// weight gradients of one stage over `nimg` images worth of rows (all timesteps at once in sequence mode).
+// The LSTM's hidden-state half is paired by the caller (it needs h_{t-1}).
+int stage_wgrads(leod_backbone *h, int s, int64_t nimg, const void *in, int x_dtype, int x_h, int x_w, const SB &b, const GB &g,
+                 cudaStream_t st) {
+  const StageD &d = h->d[s];
+  const StageP &p = h->p[s];
+  const StageW &w = h->w[s];
+  const int dt = h->cfg.dtype, C = d.C, R = h->cfg.mlp_ratio;
+  float *G = h->grads;
+  const int64_t rows_per_img = (int64_t)d.Ho * d.Wo, e = (int64_t)h->esz();
+  const int M = (int)(nimg * rows_per_img);
+  LEOD_TRY(gemm_tn(h, g.dgates, 4 * C, b.x2[1], C, G + p.lstmw, 2 * C, G + p.lstmb, M, 4 * C, C, st));
+  for (int k = 0; k < 2; ++k) {
+    const BlockP &q = p.blk[k];
+    const BlockW &bw = w.blk[k];
+    LEOD_TRY(gemm_tn(h, g.dy2[k], C, b.a[k], R * C, bw.G2, R * C, bw.s2, M, C, R * C, st));
+    LEOD_TRY(gemm_tn(h, g.du[k], R * C, b.xn2[k], C, G + q.fc1w, C, G + q.fc1b, M, R * C, C, st));
+    LEOD_TRY(gemm_tn(h, g.dy1[k], C, b.att[k], C, bw.Gproj, C, bw.sproj, M, C, C, st));
+    LEOD_TRY(gemm_tn(h, g.dqkv[k], 3 * C, k == 1 ? b.xn1 : b.x0, C, G + q.qkvw, C, G + q.qkvb, M, 3 * C, C, st));
+  }
+  const int64_t chunk_imgs = std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
+  for (int64_t i0 = 0; i0 < nimg; i0 += chunk_imgs) {
+    const int n = (int)std::min<int64_t>(chunk_imgs, nimg - i0);
+    if (s == 0) {
+      const char *xin = (const char *)in + i0 * d.Cin * x_h * x_w * (int64_t)dtype_size(x_dtype);
+      LEOD_TRY(im2col_nchw(x_dtype, dt, xin, h->ws_col, n, d.Cin, x_h, x_w, d.Hi, d.Wi, d.ksz, d.stride, d.pad, d.Kp, st));
+    } else {
+      const char *xin = (const char *)in + i0 * d.Hi * d.Wi * d.Cin * e;
+      LEOD_TRY(im2col_nhwc(dt, xin, h->ws_col, n, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, d.Kp, st));
+    }
+    // stage 0 patches are in the parameter's own (cin,ky,kx) order; later stages use (ky,kx,cin) -> scratch
+    LEOD_TRY(gemm_tn(h, (char *)g.dy0 + i0 * rows_per_img * C * e, C, h->ws_col, d.Kp, s == 0 ? G + p.convw : w.Gconv, d.K, nullptr,
+                     (int)(n * rows_per_img), C, d.K, st));
+  }
+  return 0;
+}
+
+int check_common(const leod_backbone *h, const void *x, int x_h, int x_w, int B, const char *who) {
+  LEOD_REQUIRE(h && x && B > 0, "%s: bad argument", who);
+  LEOD_REQUIRE(h->params, "%s: parameters not bound", who);
+  LEOD_REQUIRE(x_h <= h->cfg.in_h && x_w <= h->cfg.in_w && x_h > 0 && x_w > 0, "%s: input %dx%d does not fit the padded resolution %dx%d",
+               who, x_h, x_w, h->cfg.in_h, h->cfg.in_w);
+  return 0;
 }
 
 }  // namespace
@@ -292,8 +527,8 @@ extern "C" int leod_backbone_layout_only(const leod_backbone_cfg *cfg, leod_back
 extern "C" void leod_backbone_destroy(leod_backbone_t *h) {
   if (!h) return;
   for (void *p : h->owned) cudaFree(p);
-  for (void *p : {h->ws_col, h->ws_big4, h->ws_qkv, h->ws_a, h->ws_b, h->ws_c, h->ws_hint, h->ws_save})
-    if (p) cudaFree(p);
+  free_workspace(h);
+  if (h->seq_arena) cudaFree(h->seq_arena);
   delete h;
 }
 
@@ -355,160 +590,181 @@ extern "C" int leod_backbone_prepare(leod_backbone_t *h, void *stream) {
 
 extern "C" int64_t leod_backbone_save_bytes(const leod_backbone_t *h, int B) {
   if (!h || B <= 0) return -1;
-  SaveOff off[4];
+  StageLayout lay[4];
   int64_t elems;
-  compute_save_layout(h, B, off, &elems);
+  compute_layout(h, B, 1, false, false, lay, &elems);
   return elems * (int64_t)h->esz();
 }
 
 extern "C" int leod_backbone_reserve(leod_backbone_t *h, int B) {
   LEOD_REQUIRE(h && B > 0, "leod_backbone_reserve: bad argument");
-  return ensure_workspace(h, B);
+  return ensure_workspace(h, B, B);
 }
 
+// ------------------------------------------------------------------ per-timestep API
 extern "C" int leod_backbone_step_fwd(leod_backbone_t *h, const void *x, int x_dtype, int x_h, int x_w, int B,
                                       const void *const h_prev[4], const void *const c_prev[4], void *const h_out[4],
                                       void *const c_out[4], void *save, void *stream) {
-  LEOD_REQUIRE(h && x && h_out && c_out && B > 0, "leod_backbone_step_fwd: bad argument");
-  LEOD_REQUIRE(h->params, "leod_backbone_step_fwd: parameters not bound");
-  LEOD_REQUIRE(x_h <= h->cfg.in_h && x_w <= h->cfg.in_w, "input %dx%d larger than padded resolution %dx%d", x_h, x_w,
-               h->cfg.in_h, h->cfg.in_w);
+  LEOD_TRY(check_common(h, x, x_h, x_w, B, "leod_backbone_step_fwd"));
+  LEOD_REQUIRE(h_out && c_out, "leod_backbone_step_fwd: null output arrays");
   cudaStream_t st = (cudaStream_t)stream;
-  LEOD_TRY(ensure_workspace(h, B));
-  const int dt = h->cfg.dtype;
-  const float eps = h->cfg.ln_eps;
-  const float *P = h->params;
-  SaveOff off[4];
-  int64_t save_elems;
-  compute_save_layout(h, B, off, &save_elems);
+  LEOD_TRY(ensure_workspace(h, B, B));
+  StageLayout lay[4];
+  int64_t n;
+  compute_layout(h, B, 1, false, false, lay, &n);
   void *sv = save ? save : h->ws_save;
   for (int s = 0; s < 4; ++s) {
     const StageD &d = h->d[s];
-    const StageP &p = h->p[s];
-    const StageW &w = h->w[s];
-    const int M = B * d.Ho * d.Wo, C = d.C, R = h->cfg.mlp_ratio;
-    const SaveOff &o = off[s];
-    void *y0 = eoff(h, sv, o.y0), *x0 = eoff(h, sv, o.x0);
-    if (s == 0)
-      LEOD_TRY(im2col_nchw(x_dtype, dt, x, h->ws_col, B, d.Cin, x_h, x_w, d.Hi, d.Wi, d.ksz, d.stride, d.pad, d.Kp, st));
-    else
-      LEOD_TRY(im2col_nhwc(dt, h_out[s - 1], h->ws_col, B, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, d.Kp, st));
-    LEOD_TRY(gemm_nt(h, mk(h->ws_col, d.Kp, w.Wconv, d.Kp, y0, C, M, C, d.Kp), st));
-    LEOD_TRY(layernorm_fwd(dt, y0, P + p.lnw, P + p.lnb, x0, M, C, 1e-5f, st));
-    const void *xin = x0;
-    for (int b = 0; b < 2; ++b) {
-      const BlockP &q = p.blk[b];
-      const BlockW &bw = w.blk[b];
-      void *qkv = eoff(h, sv, o.blk[b].qkv), *att = eoff(h, sv, o.blk[b].att), *x1 = eoff(h, sv, o.blk[b].x1);
-      void *xn2 = eoff(h, sv, o.blk[b].xn2), *u = eoff(h, sv, o.blk[b].u), *a = eoff(h, sv, o.blk[b].a);
-      void *x2 = eoff(h, sv, o.blk[b].x2);
-      const void *ain = xin;
-      if (b == 1) {
-        void *xn1 = eoff(h, sv, o.blk[b].xn1);
-        LEOD_TRY(layernorm_fwd(dt, xin, P + q.n1w, P + q.n1b, xn1, M, C, eps, st));
-        ain = xn1;
-      }
-      LEOD_TRY(gemm_nt(h, mk(ain, C, bw.Wqkv, C, qkv, 3 * C, M, 3 * C, C, P + q.qkvb), st));
-      LEOD_TRY(attention_fwd(dt, qkv, att, B, d.Ho, d.Wo, C, h->cfg.dim_head, h->cfg.part_h, h->cfg.part_w, b == 0, st));
-      LEOD_TRY(gemm_nt(h, mk(att, C, bw.Wproj, C, x1, C, M, C, C, bw.bproj, EPI_RESID, xin, C), st));
-      LEOD_TRY(layernorm_fwd(dt, x1, P + q.n2w, P + q.n2b, xn2, M, C, eps, st));
-      LEOD_TRY(gemm_nt(h, mk(xn2, C, bw.W1, C, a, R * C, M, R * C, C, P + q.fc1b, EPI_GELU, nullptr, 0, u, R * C), st));
-      LEOD_TRY(gemm_nt(h, mk(a, R * C, bw.W2, R * C, x2, C, M, C, R * C, bw.b2, EPI_RESID, x1, C), st));
-      xin = x2;
-    }
-    void *gates = eoff(h, sv, o.gates);
-    GemmNT g = mk(xin, C, w.Wl, 2 * C, gates, 4 * C, M, 4 * C, C, P + p.lstmb);
-    const void *hp = h_prev ? h_prev[s] : nullptr;
-    if (hp) {
-      g.A2 = hp; g.lda2 = C; g.K = 2 * C; g.K1 = C;
-    }
-    LEOD_TRY(gemm_nt(h, g, st));
-    LEOD_TRY(lstm_pointwise_fwd(dt, gates, c_prev ? c_prev[s] : nullptr, h_out[s], c_out[s], M, C, st));
+    const int M = B * d.Ho * d.Wo;
+    const SB b = sb_at(h, sv, lay[s], s, B, 0);
+    LEOD_TRY(front_fwd(h, s, B, s == 0 ? x : h_out[s - 1], x_dtype, x_h, x_w, b, st));
+    LEOD_TRY(lstm_fwd(h, s, M, b.x2[1], h_prev ? h_prev[s] : nullptr, c_prev ? c_prev[s] : nullptr, b.gates, h_out[s], c_out[s], st));
   }
   return 0;
 }
 
 extern "C" int leod_backbone_step_bwd(leod_backbone_t *h, const void *x, int x_dtype, int x_h, int x_w, int B,
                                       const void *const h_prev[4], const void *const c_prev[4], const void *const h_out[4],
-                                      const void *const c_out[4], const void *save, const void *const dh_out[4], const void *const dc_out[4],
-                                      void *const dh_prev[4], void *const dc_prev[4], void *stream) {
-  LEOD_REQUIRE(h && x && save && h_out && c_out && dc_prev && B > 0, "leod_backbone_step_bwd: bad argument");
-  LEOD_REQUIRE(h->params && h->grads, "leod_backbone_step_bwd: parameter/gradient buffers not bound");
+                                      const void *const c_out[4], const void *save, const void *const dh_out[4],
+                                      const void *const dc_out[4], void *const dh_prev[4], void *const dc_prev[4], void *stream) {
+  LEOD_TRY(check_common(h, x, x_h, x_w, B, "leod_backbone_step_bwd"));
+  LEOD_REQUIRE(save && h_out && c_out && dc_prev, "leod_backbone_step_bwd: null argument");
+  LEOD_REQUIRE(h->grads, "leod_backbone_step_bwd: gradient buffer not bound");
   cudaStream_t st = (cudaStream_t)stream;
-  LEOD_TRY(ensure_workspace(h, B));
-  const int dt = h->cfg.dtype;
-  const float eps = h->cfg.ln_eps;
-  const float *P = h->params;
-  float *G = h->grads;
-  SaveOff off[4];
-  int64_t save_elems;
-  compute_save_layout(h, B, off, &save_elems);
-  const void *sv = save;
-  bool have_hint = false;  // gradient flowing down from stage s+1's conv into h_out[s]
+  LEOD_TRY(ensure_workspace(h, B, B));
+  StageLayout lay[4], glay[4];
+  int64_t n;
+  compute_layout(h, B, 1, false, false, lay, &n);
+  compute_layout(h, B, 1, true, false, glay, &n);
+  bool have_hint = false;
   for (int s = 3; s >= 0; --s) {
     const StageD &d = h->d[s];
-    const StageP &p = h->p[s];
-    const StageW &w = h->w[s];
-    const int M = B * d.Ho * d.Wo, C = d.C, R = h->cfg.mlp_ratio;
-    const SaveOff &o = off[s];
-    const void *gates = eoff(h, sv, o.gates);
-    const void *x2last = eoff(h, sv, o.blk[1].x2);
+    const int M = B * d.Ho * d.Wo, C = d.C;
+    const SB b = sb_at(h, save, lay[s], s, B, 0);
+    const GB g = gb_at(h, h->ws_stash, glay[s], s, B, 0);
     const void *hp = h_prev ? h_prev[s] : nullptr;
-    void *dgates = h->ws_big4;
-    // ---- LSTM
-    LEOD_TRY(lstm_pointwise_bwd(dt, gates, c_prev ? c_prev[s] : nullptr, c_out[s], dh_out ? dh_out[s] : nullptr,
-                                have_hint ? h->ws_hint : nullptr, dc_out ? dc_out[s] : nullptr, dgates, dc_prev[s], M, C, st));
-    LEOD_TRY(gemm_tn(h, dgates, 4 * C, x2last, C, G + p.lstmw, 2 * C, G + p.lstmb, M, 4 * C, C, st));
-    if (hp) LEOD_TRY(gemm_tn(h, dgates, 4 * C, hp, C, G + p.lstmw + C, 2 * C, nullptr, M, 4 * C, C, st));
-    void *dy = h->ws_a, *dy1 = h->ws_b, *dxn = h->ws_c;
-    LEOD_TRY(gemm_nt(h, mk(dgates, 4 * C, w.WlT, 4 * C, dy, C, M, C, 4 * C), st));
-    if (dh_prev && dh_prev[s])
-      LEOD_TRY(gemm_nt(h, mk(dgates, 4 * C, eoff(h, w.WlT, (int64_t)C * 4 * C), 4 * C, dh_prev[s], C, M, C, 4 * C), st));
-    // ---- attention blocks, grid then window
-    for (int b = 1; b >= 0; --b) {
-      const BlockP &q = p.blk[b];
-      const BlockW &bw = w.blk[b];
-      const void *qkv = eoff(h, sv, o.blk[b].qkv), *att = eoff(h, sv, o.blk[b].att), *x1 = eoff(h, sv, o.blk[b].x1);
-      const void *xn2 = eoff(h, sv, o.blk[b].xn2), *u = eoff(h, sv, o.blk[b].u), *a = eoff(h, sv, o.blk[b].a);
-      const void *xin = (b == 1) ? eoff(h, sv, o.blk[0].x2) : eoff(h, sv, o.x0);
-      void *du = h->ws_big4, *dqkv = h->ws_qkv;
-      // MLP: x2 = x1 + W2'(gelu(W1 xn2 + b1)) + b2'
-      LEOD_TRY(gemm_tn(h, dy, C, a, R * C, bw.G2, R * C, bw.s2, M, C, R * C, st));
-      LEOD_TRY(gemm_nt(h, mk(dy, C, bw.W2T, C, du, R * C, M, R * C, C, nullptr, EPI_GELU_BWD, nullptr, 0, (void *)u, R * C), st));
-      LEOD_TRY(gemm_tn(h, du, R * C, xn2, C, G + q.fc1w, C, G + q.fc1b, M, R * C, C, st));
-      LEOD_TRY(gemm_nt(h, mk(du, R * C, bw.W1T, R * C, dxn, C, M, C, R * C), st));
-      LEOD_TRY(layernorm_bwd(dt, x1, P + q.n2w, dxn, dy, dy1, G + q.n2w, G + q.n2b, M, C, eps, st));
-      // attention: x1 = xin + Wp'(attn(Wqkv LN1(xin))) + bp'
-      LEOD_TRY(gemm_tn(h, dy1, C, att, C, bw.Gproj, C, bw.sproj, M, C, C, st));
-      LEOD_TRY(gemm_nt(h, mk(dy1, C, bw.WprojT, C, dxn, C, M, C, C), st));
-      LEOD_TRY(attention_bwd(dt, qkv, dxn, dqkv, B, d.Ho, d.Wo, C, h->cfg.dim_head, h->cfg.part_h, h->cfg.part_w, b == 0, st));
-      if (b == 1) {
-        const void *xn1 = eoff(h, sv, o.blk[b].xn1);
-        LEOD_TRY(gemm_tn(h, dqkv, 3 * C, xn1, C, G + q.qkvw, C, G + q.qkvb, M, 3 * C, C, st));
-        LEOD_TRY(gemm_nt(h, mk(dqkv, 3 * C, bw.WqkvT, 3 * C, dxn, C, M, C, 3 * C), st));
-        LEOD_TRY(layernorm_bwd(dt, xin, P + q.n1w, dxn, dy1, dy, G + q.n1w, G + q.n1b, M, C, eps, st));
-      } else {
-        LEOD_TRY(gemm_tn(h, dqkv, 3 * C, xin, C, G + q.qkvw, C, G + q.qkvb, M, 3 * C, C, st));
-        LEOD_TRY(gemm_nt(h, mk(dqkv, 3 * C, bw.WqkvT, 3 * C, dy, C, M, C, 3 * C, nullptr, EPI_RESID, dy1, C), st));
+    LEOD_TRY(lstm_bwd(h, s, M, b.gates, c_prev ? c_prev[s] : nullptr, c_out[s], dh_out ? dh_out[s] : nullptr,
+                      have_hint ? h->ws_hint : nullptr, nullptr, dc_out ? dc_out[s] : nullptr, g, dc_prev[s],
+                      (dh_prev && dh_prev[s]) ? dh_prev[s] : nullptr, st));
+    LEOD_TRY(front_bwd(h, s, B, b, g, s > 0 ? h->ws_hint : nullptr, st));
+    have_hint = s > 0;
+    LEOD_TRY(stage_wgrads(h, s, B, s == 0 ? x : h_out[s - 1], x_dtype, x_h, x_w, b, g, st));
+    if (hp) LEOD_TRY(gemm_tn(h, g.dgates, 4 * C, hp, C, h->grads + h->p[s].lstmw + C, 2 * C, nullptr, M, 4 * C, C, st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ sequence (BPTT window) API
+static int ensure_seq(leod_backbone *h, int B, int L) {
+  LEOD_TRY(ensure_workspace(h, (int64_t)B * L, B));
+  if (h->seq_arena && h->seq_B == B && h->seq_L == L) return 0;
+  if (h->seq_arena) cudaFree(h->seq_arena);
+  h->seq_arena = nullptr;
+  StageLayout lay[4];
+  int64_t n;
+  compute_layout(h, B, L, true, true, lay, &n);
+  LEOD_CUDA(cudaMalloc(&h->seq_arena, n * (int64_t)h->esz()));
+  h->seq_B = B;
+  h->seq_L = L;
+  return 0;
+}
+
+extern "C" int64_t leod_backbone_seq_arena_bytes(const leod_backbone_t *h, int B, int L) {
+  if (!h || B <= 0 || L <= 0) return -1;
+  StageLayout lay[4];
+  int64_t n;
+  compute_layout(h, B, L, true, true, lay, &n);
+  return n * (int64_t)h->esz();
+}
+
+extern "C" int leod_backbone_seq_fwd(leod_backbone_t *h, const void *x, int x_dtype, int x_h, int x_w, int B, int L,
+                                     const void *const h0[4], const void *const c0[4], void *const h_all[4], void *const c_last[4],
+                                     void *stream) {
+  LEOD_TRY(check_common(h, x, x_h, x_w, B, "leod_backbone_seq_fwd"));
+  LEOD_REQUIRE(L > 0 && h_all && c_last, "leod_backbone_seq_fwd: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  LEOD_TRY(ensure_seq(h, B, L));
+  StageLayout lay[4];
+  int64_t n;
+  compute_layout(h, B, L, true, true, lay, &n);
+  const int64_t e = (int64_t)h->esz();
+  // stage 1 up to its LSTM does not depend on the recurrent state: all L*B frames in one batch
+  const SB b0 = sb_at(h, h->seq_arena, lay[0], 0, B, 0);
+  LEOD_TRY(front_fwd(h, 0, (int64_t)B * L, x, x_dtype, x_h, x_w, b0, st));
+  for (int t = 0; t < L; ++t) {
+    for (int s = 0; s < 4; ++s) {
+      const StageD &d = h->d[s];
+      const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
+      const SB b = sb_at(h, h->seq_arena, lay[s], s, B, t);
+      char *hs = (char *)h_all[s];
+      char *cs = (char *)h->seq_arena + lay[s].c_all * e;
+      const void *hp = t == 0 ? (h0 ? h0[s] : nullptr) : hs + (t - 1) * M * C * e;
+      const void *cp = t == 0 ? (c0 ? c0[s] : nullptr) : cs + (t - 1) * M * C * e;
+      if (s > 0) LEOD_TRY(front_fwd(h, s, B, (char *)h_all[s - 1] + (int64_t)t * B * d.Hi * d.Wi * d.Cin * e, 0, 0, 0, b, st));
+      LEOD_TRY(lstm_fwd(h, s, (int)M, b.x2[1], hp, cp, b.gates, hs + t * M * C * e, cs + t * M * C * e, st));
+    }
+  }
+  for (int s = 0; s < 4; ++s) {
+    const StageD &d = h->d[s];
+    const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
+    LEOD_CUDA(cudaMemcpyAsync(c_last[s], (char *)h->seq_arena + (lay[s].c_all + (L - 1) * M * C) * e, M * C * e, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+extern "C" int leod_backbone_seq_bwd(leod_backbone_t *h, const void *x, int x_dtype, int x_h, int x_w, int B, int L,
+                                     const void *const h0[4], const void *const c0[4], const void *const h_all[4],
+                                     const void *const dh_all[4], const void *const dc_last[4], void *const dh0[4], void *const dc0[4],
+                                     void *stream) {
+  LEOD_TRY(check_common(h, x, x_h, x_w, B, "leod_backbone_seq_bwd"));
+  LEOD_REQUIRE(L > 0 && h_all, "leod_backbone_seq_bwd: bad argument");
+  LEOD_REQUIRE(h->grads, "leod_backbone_seq_bwd: gradient buffer not bound");
+  LEOD_REQUIRE(h->seq_arena && h->seq_B == B && h->seq_L == L, "leod_backbone_seq_bwd: no matching leod_backbone_seq_fwd (B=%d L=%d)", B, L);
+  cudaStream_t st = (cudaStream_t)stream;
+  StageLayout lay[4];
+  int64_t n;
+  compute_layout(h, B, L, true, true, lay, &n);
+  const int64_t e = (int64_t)h->esz();
+  for (int t = L - 1; t >= 0; --t) {
+    bool have_hint = false;
+    for (int s = 3; s >= 0; --s) {
+      const StageD &d = h->d[s];
+      const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
+      const SB b = sb_at(h, h->seq_arena, lay[s], s, B, t);
+      const GB g = gb_at(h, h->seq_arena, lay[s], s, B, t);
+      const char *cs = (const char *)h->seq_arena + lay[s].c_all * e;
+      const void *cp = t == 0 ? (c0 ? c0[s] : nullptr) : cs + (t - 1) * M * C * e;
+      const void *dh_head = (dh_all && dh_all[s]) ? (const char *)dh_all[s] + t * M * C * e : nullptr;
+      const void *dh_next = t < L - 1 ? h->ws_dhc[s] : nullptr;            // from timestep t+1
+      const void *dc_in = t < L - 1 ? h->ws_dcc[s] : (dc_last ? dc_last[s] : nullptr);
+      const bool has_hp = t > 0 || (h0 && h0[s]);
+      void *dc_out_ptr = (t == 0 && dc0 && dc0[s]) ? dc0[s] : h->ws_dcc[s];
+      void *dh_out_ptr = !has_hp ? nullptr : ((t == 0) ? ((dh0 && dh0[s]) ? dh0[s] : nullptr) : h->ws_dhc[s]);
+      LEOD_TRY(lstm_bwd(h, s, (int)M, b.gates, cp, cs + t * M * C * e, dh_head, have_hint ? h->ws_hint : nullptr, dh_next, dc_in, g,
+                        dc_out_ptr, dh_out_ptr, st));
+      if (s > 0) {
+        LEOD_TRY(front_bwd(h, s, B, b, g, h->ws_hint, st));
+        have_hint = true;
       }
     }
-    // ---- downsample: x0 = LN(conv(in))
-    const void *y0 = eoff(h, sv, o.y0);
-    void *dy0 = h->ws_b;
-    LEOD_TRY(layernorm_bwd(dt, y0, P + p.lnw, dy, nullptr, dy0, G + p.lnw, G + p.lnb, M, C, 1e-5f, st));
-    if (s == 0) {
-      LEOD_TRY(im2col_nchw(x_dtype, dt, x, h->ws_col, B, d.Cin, x_h, x_w, d.Hi, d.Wi, d.ksz, d.stride, d.pad, d.Kp, st));
-      LEOD_TRY(gemm_tn(h, dy0, C, h->ws_col, d.Kp, G + p.convw, d.K, nullptr, M, C, d.K, st));
-      have_hint = false;
-    } else {
-      // weight gradient in the (ky,kx,cin) patch order -> scratch, un-permuted in grads_finalize
-      LEOD_TRY(im2col_nhwc(dt, h_out[s - 1], h->ws_col, B, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, d.Kp, st));
-      LEOD_TRY(gemm_tn(h, dy0, C, h->ws_col, d.Kp, w.Gconv, d.K, nullptr, M, C, d.K, st));
-      // input gradient: dcol = dy0 * Wconv, then gather-scatter back to the stage s-1 map
-      LEOD_TRY(gemm_nt(h, mk(dy0, C, w.WconvT, C, h->ws_col, d.Kp, M, d.K, C), st));
-      LEOD_TRY(col2im_nhwc(dt, h->ws_col, d.Kp, nullptr, h->ws_hint, B, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, st));
-      have_hint = true;
-    }
+  }
+  // stage 1 blocks + stem for the whole window at once
+  {
+    const SB b = sb_at(h, h->seq_arena, lay[0], 0, B, 0);
+    const GB g = gb_at(h, h->seq_arena, lay[0], 0, B, 0);
+    LEOD_TRY(front_bwd(h, 0, (int64_t)B * L, b, g, nullptr, st));
+  }
+  // weight gradients: one GEMM per layer over all L timesteps
+  for (int s = 0; s < 4; ++s) {
+    const StageD &d = h->d[s];
+    const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
+    const SB b = sb_at(h, h->seq_arena, lay[s], s, B, 0);
+    const GB g = gb_at(h, h->seq_arena, lay[s], s, B, 0);
+    LEOD_TRY(stage_wgrads(h, s, (int64_t)B * L, s == 0 ? x : h_all[s - 1], x_dtype, x_h, x_w, b, g, st));
+    float *dWl_h = h->grads + h->p[s].lstmw + C;
+    if (L > 1)   // dgates of timesteps 1..L-1 pair with the hidden states of timesteps 0..L-2
+      LEOD_TRY(gemm_tn(h, (char *)g.dgates + M * 4 * C * e, 4 * C, h_all[s], C, dWl_h, 2 * C, nullptr, (int)((L - 1) * M), 4 * C, C, st));
+    if (h0 && h0[s]) LEOD_TRY(gemm_tn(h, g.dgates, 4 * C, h0[s], C, dWl_h, 2 * C, nullptr, (int)M, 4 * C, C, st));
   }
   return 0;
 }

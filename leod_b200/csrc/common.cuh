@@ -122,7 +122,7 @@ int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, cons
 int lstm_pointwise_fwd(int dtype, void *gates /*in: pre-act, out: activated*/, const void *c_prev, void *h_out, void *c_out,
                        int M, int C, cudaStream_t st);
 int lstm_pointwise_bwd(int dtype, const void *gates, const void *c_prev, const void *c_out, const void *dh, const void *dh2,
-                       const void *dc, void *dgates, void *dc_prev, int M, int C, cudaStream_t st);
+                       const void *dc, void *dgates, void *dc_prev, int M, int C, cudaStream_t st, const void *dh3 = nullptr);
 int add_tensors(int dtype, const void *a, const void *b, void *out, int64_t n, cudaStream_t st);
 int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin, int xh, int xw, int Hp, int Wp, int ksz,
                 int stride, int pad, int ldcol, cudaStream_t st);

@@ -142,8 +142,8 @@ __global__ void lstm_fwd_kernel(T *__restrict__ gates, const T *__restrict__ c_p
 
 template <typename T>
 __global__ void lstm_bwd_kernel(const T *__restrict__ gates, const T *__restrict__ c_prev, const T *__restrict__ c_out,
-                                const T *__restrict__ dh, const T *__restrict__ dh2, const T *__restrict__ dc,
-                                T *__restrict__ dgates, T *__restrict__ dc_prev, int M, int C) {
+                                const T *__restrict__ dh, const T *__restrict__ dh2, const T *__restrict__ dh3,
+                                const T *dc, T *__restrict__ dgates, T *dc_prev, int M, int C) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)M * C) return;
   const int m = (int)(idx / C), c = (int)(idx % C);
@@ -153,6 +153,7 @@ __global__ void lstm_bwd_kernel(const T *__restrict__ gates, const T *__restrict
   const float tc = tanhf(to_f<T>(c_out[idx]));
   float dhv = dh ? to_f<T>(dh[idx]) : 0.f;
   if (dh2) dhv += to_f<T>(dh2[idx]);
+  if (dh3) dhv += to_f<T>(dh3[idx]);
   float dcv = dc ? to_f<T>(dc[idx]) : 0.f;
   dcv += dhv * o * (1.f - tc * tc);
   T *dg = dgates + (size_t)m * 4 * C;
@@ -383,12 +384,12 @@ int lstm_pointwise_fwd(int dtype, void *gates, const void *c_prev, void *h_out, 
 }
 
 int lstm_pointwise_bwd(int dtype, const void *gates, const void *c_prev, const void *c_out, const void *dh, const void *dh2,
-                       const void *dc, void *dgates, void *dc_prev, int M, int C, cudaStream_t st) {
+                       const void *dc, void *dgates, void *dc_prev, int M, int C, cudaStream_t st, const void *dh3) {
   ProfScope ps(PK_LSTM, 30.0 * M * C, 13.0 * M * C * dtype_size(dtype), st);
   const int64_t n = (int64_t)M * C;
   DISPATCH_T(dtype, (lstm_bwd_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)gates, (const T *)c_prev, (const T *)c_out,
-                                                                           (const T *)dh, (const T *)dh2, (const T *)dc,
-                                                                           (T *)dgates, (T *)dc_prev, M, C)));
+                                                                           (const T *)dh, (const T *)dh2, (const T *)dh3,
+                                                                           (const T *)dc, (T *)dgates, (T *)dc_prev, M, C)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }

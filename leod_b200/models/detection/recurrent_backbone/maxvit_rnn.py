@@ -66,6 +66,25 @@ class _BackboneStep(torch.autograd.Function):
         return (None, None, None) + tuple(d if m else None for d, m in zip(dstates, ctx.state_mask))
 
 
+class _BackboneSeq(torch.autograd.Function):
+    """A whole BPTT window (leod_backbone_seq_fwd / _bwd): x [L,B,C,H,W] -> h of every timestep, final c."""
+
+    @staticmethod
+    def forward(ctx, bb, anchor, x, *states):
+        outs, keep = bb._seq_forward(x, states)
+        ctx.bb = bb
+        ctx.keep = keep
+        ctx.state_mask = [s is not None for s in states]
+        ctx.save_for_backward(*outs[:4])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        dstates = ctx.bb._seq_backward(ctx.keep, ctx.saved_tensors, grads)
+        ctx.keep = None
+        return (None, None, None) + tuple(d if m else None for d, m in zip(dstates, ctx.state_mask))
+
+
 class RNNDetector(nn.Module):
     """RNN-based backbone with MaxViT blocks (reference: maxvit_rnn.py:23)."""
 
@@ -363,6 +382,78 @@ class RNNDetector(nn.Module):
             res.append(dprev[2 * s].permute(0, 3, 1, 2) if h_prev[s] is not None else None)
             res.append(dprev[2 * s + 1].permute(0, 3, 1, 2) if c_prev[s] is not None else None)
         return res
+
+    # ------------------------------------------------------------------ whole-window fast path
+    def _seq_forward(self, x, states):
+        l = _lib.lib()
+        L, B = x.shape[0], x.shape[1]
+        dev = x.device
+        shapes = self._state_shapes(B)
+        if x.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
+            x = x.float()
+        x = x.contiguous()
+        st = [self._nhwc(states[i], shapes[i // 2]) for i in range(8)]
+        h0, c0 = [st[2 * s] for s in range(4)], [st[2 * s + 1] for s in range(4)]
+        h_all = [torch.empty((L, shp[0], shp[2], shp[3], shp[1]), dtype=self.compute_dtype, device=dev) for shp in shapes]
+        c_last = [torch.empty((shp[0], shp[2], shp[3], shp[1]), dtype=self.compute_dtype, device=dev) for shp in shapes]
+        with torch.cuda.device(dev):
+            _lib.check(l.leod_backbone_seq_fwd(self._handle, _lib.ptr(x), _lib.leod_dtype(x.dtype), x.shape[3], x.shape[4], B, L,
+                                               _lib.vp4(h0), _lib.vp4(c0), _lib.vp4(h_all), _lib.vp4(c_last),
+                                               _lib.stream_ptr(dev)), 'backbone_seq_fwd')
+        outs = [t.permute(0, 1, 4, 2, 3) for t in h_all] + [t.permute(0, 3, 1, 2) for t in c_last]
+        return outs, (x, h0, c0)
+
+    def _seq_backward(self, keep, h_all_views, grads):
+        l = _lib.lib()
+        x, h0, c0 = keep
+        L, B = x.shape[0], x.shape[1]
+        dev = x.device
+        shapes = self._state_shapes(B)
+        self._begin_backward_pass()
+        h_all = [v.permute(0, 1, 3, 4, 2) for v in h_all_views]
+        dh_all = []
+        for s in range(4):
+            g = grads[s]
+            if g is not None:
+                g = g.permute(0, 1, 3, 4, 2)
+                if g.dtype != self.compute_dtype:
+                    g = g.to(self.compute_dtype)
+                g = g if g.is_contiguous() else g.contiguous()
+            dh_all.append(g)
+        dc_last = [self._nhwc(grads[4 + s], shapes[s]) for s in range(4)]
+        dh0 = [torch.empty_like(h0[s]) if h0[s] is not None else None for s in range(4)]
+        dc0 = [torch.empty_like(c0[s]) if c0[s] is not None else None for s in range(4)]
+        with torch.cuda.device(dev):
+            _lib.check(l.leod_backbone_seq_bwd(self._handle, _lib.ptr(x), _lib.leod_dtype(x.dtype), x.shape[3], x.shape[4], B, L,
+                                               _lib.vp4(h0), _lib.vp4(c0), _lib.vp4(h_all), _lib.vp4(dh_all), _lib.vp4(dc_last),
+                                               _lib.vp4(dh0), _lib.vp4(dc0), _lib.stream_ptr(dev)), 'backbone_seq_bwd')
+        res = []
+        for s in range(4):
+            res.append(dh0[s].permute(0, 3, 1, 2) if dh0[s] is not None else None)
+            res.append(dc0[s].permute(0, 3, 1, 2) if dc0[s] is not None else None)
+        return res
+
+    def forward_sequence(self, x: torch.Tensor, prev_states: Optional[List[Optional[LstmState]]] = None) \
+            -> Tuple[Dict[int, torch.Tensor], List[LstmState]]:
+        """All L timesteps of a batch in one call (the loop of modules/detection.py:188-224 moved into the
+        library).  x: [L,B,C,H,W] (uint8 / float).  Returns ({stage: [L,B,C,h,w] features of every timestep},
+        [(h_L, c_L)]*4).  Numerically identical to calling `forward` L times; one backward per forward."""
+        assert x.dim() == 5 and x.shape[2] == self.in_channels, x.shape
+        self.prepare()
+        if prev_states is None:
+            prev_states = [None] * 4
+        flat_states = []
+        for st in prev_states:
+            flat_states.extend((None, None) if st is None else (st[0], st[1]))
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p, *_ in self._param_views)
+        if need_grad:
+            self._ensure_grad_buffer()
+            outs = _BackboneSeq.apply(self, self._anchor, x, *flat_states)
+        else:
+            outs, _ = self._seq_forward(x, flat_states)
+        feats = {s + 1: outs[s] for s in range(4)}
+        states = [(outs[s][-1], outs[4 + s]) for s in range(4)]
+        return feats, states
 
     # ------------------------------------------------------------------ gradient hand-over
     def _begin_backward_pass(self):

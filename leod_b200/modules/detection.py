@@ -54,6 +54,8 @@ class Module(_Base):
         self.label_subsample_idx = get_subsample_label_idx(L=L, use_every=self.mdl_config.get('use_label_every', 1))
         self.mode_2_rnn_states: Dict[Mode, RNNStates] = {m: RNNStates() for m in Mode}
         self._opt_state = None
+        # True: one library call per BPTT window (forward_sequence); False: the reference's per-timestep calls
+        self.use_sequence_kernel = True
 
     # ------------------------------------------------------------------ data
     def get_data_from_batch(self, batch: Any):
@@ -74,22 +76,38 @@ class Module(_Base):
         assert L > 0
         B = len(sparse_obj_labels[0])
         prev_states = self.mode_2_rnn_states[mode].get_states(worker_id=worker_id)
-        selector = BackboneFeatureSelector()
         obj_labels = []
         ignore = self.mdl_config.get('ignore_image', False)
         ignore_label = self.mdl_config.head.get('ignore_label', 1024)
-        for tidx in range(L):
-            feats, states = self.mdl.forward_backbone(x=ev_seq[tidx], previous_states=prev_states, token_mask=None)
-            prev_states = states
-            current_labels, valid_idx = sparse_obj_labels[tidx].get_valid_labels_and_batch_indices(
-                ignore=ignore, ignore_label=ignore_label)
-            if len(current_labels) > 0:
-                selector.add_backbone_features(backbone_features=feats,
-                                               selected_indices=None if len(valid_idx) == B and valid_idx == list(range(B)) else valid_idx)
-                obj_labels.extend(current_labels)
+        if self.use_sequence_kernel:
+            # the time loop of modules/detection.py:188-224 runs inside the library (one call per window)
+            ev = ev_seq if torch.is_tensor(ev_seq) else torch.stack(list(ev_seq))
+            feats_all, prev_states = self.mdl.backbone.forward_sequence(ev, prev_states)
+            t_idx, b_idx = [], []
+            for tidx in range(L):
+                current_labels, valid_idx = sparse_obj_labels[tidx].get_valid_labels_and_batch_indices(
+                    ignore=ignore, ignore_label=ignore_label)
+                if len(current_labels) > 0:
+                    obj_labels.extend(current_labels)
+                    t_idx.extend([tidx] * len(valid_idx))
+                    b_idx.extend(valid_idx)
+            assert len(obj_labels) > 0
+            ti = torch.as_tensor(t_idx, device=ev.device)
+            bi = torch.as_tensor(b_idx, device=ev.device)
+            sel = {k: v[ti, bi] for k, v in feats_all.items() if k in self.mdl.fpn.in_features}
+        else:
+            selector = BackboneFeatureSelector()
+            for tidx in range(L):
+                feats, states = self.mdl.forward_backbone(x=ev_seq[tidx], previous_states=prev_states, token_mask=None)
+                prev_states = states
+                current_labels, valid_idx = sparse_obj_labels[tidx].get_valid_labels_and_batch_indices(
+                    ignore=ignore, ignore_label=ignore_label)
+                if len(current_labels) > 0:
+                    selector.add_backbone_features(backbone_features=feats, selected_indices=valid_idx)
+                    obj_labels.extend(current_labels)
+            sel = selector.get_batched_backbone_features()
         self.mode_2_rnn_states[mode].save_states_and_detach(worker_id=worker_id, states=prev_states)
         assert len(obj_labels) > 0
-        sel = selector.get_batched_backbone_features()
         labels_yolox = type(obj_labels[0]).get_labels_as_batched_tensor(obj_label_list=obj_labels, format_='yolox')
         labels_yolox = labels_yolox.to(device=ev_seq[0].device, dtype=torch.float32)
         predictions, losses = self.mdl.forward_detect(backbone_features=sel, targets=labels_yolox)

@@ -117,6 +117,100 @@ def test_backbone_gradients_smooth_loss_vs_oracle(net, dtype, impl):
     assert errs[len(errs) // 2] < GRAD_TOL[dtype] / 4
 
 
+@pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
+def test_sequence_kernel_equals_per_step_calls(net, dtype):
+    """forward_sequence (one library call per BPTT window, stage 1 batched over time, deferred weight gradients)
+    against L calls of the per-timestep interface: same features, same final states, same parameter and
+    initial-state gradients — also when the window starts from a carried state."""
+    z, cfg, sd, d = net
+    m = build(cfg, sd, (d['H'], d['W']), dtype).train()
+    bb = m.backbone
+    x = torch.from_numpy(z['x']).cuda()
+    T = d['T']
+    g = torch.Generator(device='cuda').manual_seed(1)
+    with torch.no_grad():
+        _, warm = bb(x[0], None)
+    init = [(h.detach().clone().requires_grad_(True), c.detach().clone().requires_grad_(True)) for h, c in warm]
+    R = None
+    results = []
+    for mode in ('step', 'seq'):
+        for start in (None, init):
+            m.zero_grad(set_to_none=True)
+            if start is not None:
+                for h, c in start:
+                    h.grad = c.grad = None
+            if mode == 'step':
+                states, hs = start, {k: [] for k in (1, 2, 3, 4)}
+                for t in range(T):
+                    f, states = bb(x[t], states)
+                    for k in hs:
+                        hs[k].append(f[k])
+                feats = {k: torch.stack(v) for k, v in hs.items()}
+            else:
+                feats, states = bb.forward_sequence(x, start)
+            if R is None:
+                R = ({k: torch.randn(v.shape, device='cuda', generator=g) for k, v in feats.items()},
+                     [torch.randn(c.shape, device='cuda', generator=g) for _, c in states])
+            loss = sum((feats[k].float() * R[0][k]).sum() for k in feats) + sum((c.float() * r).sum() for (_, c), r in zip(states, R[1]))
+            loss.backward()
+            torch.cuda.synchronize()
+            results.append(dict(feats={k: v.detach().float().clone() for k, v in feats.items()},
+                                c=[c.detach().float().clone() for _, c in states], grads=bb.flat_grads.clone(),
+                                dinit=None if start is None else [t.grad.float().clone() for hc in start for t in hc]))
+    tol = 1e-5 if dtype == 'fp32' else 2e-3
+    for a, b in ((results[0], results[2]), (results[1], results[3])):
+        for k in a['feats']:
+            assert rel_err(b['feats'][k], a['feats'][k]) < tol, k
+        for ca, cb in zip(a['c'], b['c']):
+            assert rel_err(cb, ca) < tol
+        assert rel_err(b['grads'], a['grads']) < (1e-4 if dtype == 'fp32' else 1e-2)
+        if a['dinit'] is not None:
+            for ga, gb_ in zip(a['dinit'], b['dinit']):
+                assert rel_err(gb_, ga) < (1e-4 if dtype == 'fp32' else 1e-2)
+
+
+def test_training_step_module_sequence_vs_per_step(net):
+    """leod_b200.modules.detection.Module.training_step on the reference's batch-dict contract: the fast
+    (sequence kernel) and the per-timestep code path give the same loss and gradients."""
+    from leod_b200.config import Node
+    from leod_b200.data.labels import ObjectLabels, SparselyBatchedObjectLabels
+    from leod_b200.data.utils.types import DataType
+    from leod_b200.modules.detection import Module
+    z, cfg, sd, d = net
+    full = Node(model=product_cfg(cfg, (d['H'], d['W']), compute_dtype='fp32'), dataset=dict(sequence_length=d['T'], name='gen1'))
+    mod = Module(full)
+    mod.mdl.load_state_dict(sd)
+    mod.cuda().train()
+    x = torch.from_numpy(z['x']).cuda()
+    lab = torch.from_numpy(z['train_plain/labels'])       # [B,N,7] yolox rows on the last frame
+    B = x.shape[1]
+    seq_labels = []
+    for t in range(d['T']):
+        row = []
+        for b in range(B):
+            if t != d['T'] - 1:
+                row.append(None)
+                continue
+            l = lab[b][lab[b].sum(1) > 0]
+            rows8 = torch.stack((torch.ones(len(l)), l[:, 1] - l[:, 3] / 2, l[:, 2] - l[:, 4] / 2, l[:, 3], l[:, 4], l[:, 0], l[:, 6], l[:, 5]), 1)
+            row.append(ObjectLabels(rows8, (d['H'], d['W'])))
+        seq_labels.append(SparselyBatchedObjectLabels(row))
+    out = {}
+    for fast in (False, True):
+        mod.use_sequence_kernel = fast
+        mod.zero_grad(set_to_none=True)
+        mod.mode_2_rnn_states = {k: type(v)() for k, v in mod.mode_2_rnn_states.items()}
+        batch = {'worker_id': 0, 'data': {DataType.EV_REPR: [x[t] for t in range(d['T'])], DataType.OBJLABELS_SEQ: seq_labels,
+                                          DataType.IS_FIRST_SAMPLE: torch.ones(B, dtype=torch.bool)}}
+        res = mod.training_step(batch)
+        res['loss'].backward()
+        torch.cuda.synchronize()
+        out[fast] = (float(res['loss']), mod.mdl.backbone.flat_grads.clone())
+    ref = float(z['train_plain/loss'])
+    assert abs(out[False][0] - ref) < 1e-3 * abs(ref) and abs(out[True][0] - ref) < 1e-3 * abs(ref)
+    assert rel_err(out[True][1], out[False][1]) < 1e-4
+
+
 def test_gradient_accumulation_and_zero_grad(net):
     z, cfg, sd, d = net
     m = build(cfg, sd, (d['H'], d['W']), 'fp32').train()
