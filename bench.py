@@ -162,6 +162,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-kinds', action='store_true', help='print the per-kernel-class breakdown to stderr')
     ap.add_argument('--profile-csv', default=None, help='write one line per launch of the roofline pass to this CSV')
+    ap.add_argument('--phases', action='store_true', help='after the timed regions, time the phases of 3 extra steps (stderr)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -298,6 +299,44 @@ def main():
             for k, v in kinds.items():
                 print(f'  {k:14s} launches {v["launches"]:5d}  {v["ms"]:8.3f} ms  {v["flops"] / 1e9:9.1f} GF  {v["bytes"] / 1e6:9.1f} MB',
                       file=sys.stderr)
+
+    if rank == 0 and args.phases:
+        marks = []
+
+        def mark(name):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+        def wrap(obj, attr, name):
+            fn = getattr(obj, attr)
+
+            def inner(*a, **k):
+                mark('pre_' + name)
+                r = fn(*a, **k)
+                mark(name)
+                return r
+            setattr(obj, attr, inner)
+            return fn
+        o1 = wrap(bb, 'forward_sequence', 'backbone_fwd')
+        o2 = wrap(module.mdl, 'forward_detect', 'neck_head_loss_fwd')
+        acc = {}
+        for i in range(3):
+            marks.clear()
+            mark('start')
+            opt.zero_grad()
+            out = module.training_step(make_batch(*resident[i % n_batches]))
+            mark('host_glue_fwd')
+            out['loss'].backward()
+            mark('backward(head+backbone)')
+            opt.step()
+            mark('optimizer')
+            torch.cuda.synchronize()
+            for (n0, e0_), (n1, e1_) in zip(marks[:-1], marks[1:]):
+                acc[n1] = acc.get(n1, 0.0) + e0_.elapsed_time(e1_) / 3
+        bb.forward_sequence, module.mdl.forward_detect = o1, o2
+        for k, v in acc.items():
+            print(f'  phase {k:28s} {v:8.3f} ms', file=sys.stderr)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -688,20 +688,28 @@ extern "C" int leod_backbone_seq_fwd(leod_backbone_t *h, const void *x, int x_dt
   int64_t n;
   compute_layout(h, B, L, true, true, lay, &n);
   const int64_t e = (int64_t)h->esz();
-  // stage 1 up to its LSTM does not depend on the recurrent state: all L*B frames in one batch
-  const SB b0 = sb_at(h, h->seq_arena, lay[0], 0, B, 0);
-  LEOD_TRY(front_fwd(h, 0, (int64_t)B * L, x, x_dtype, x_h, x_w, b0, st));
-  for (int t = 0; t < L; ++t) {
-    for (int s = 0; s < 4; ++s) {
-      const StageD &d = h->d[s];
-      const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
-      const SB b = sb_at(h, h->seq_arena, lay[s], s, B, t);
-      char *hs = (char *)h_all[s];
-      char *cs = (char *)h->seq_arena + lay[s].c_all * e;
+  // Stage-major ("layer-wise") schedule.  Stage s at time t needs stage s-1 at time t and its own state at t-1; there
+  // is no top-down feedback, so a whole stage can run over all L timesteps before the next one starts.  Everything but
+  // the hidden-state half of the ConvLSTM gates is then batched over the L*B frames of the window; only
+  // gates_t += W_h h_{t-1} and the gate math remain sequential.
+  for (int s = 0; s < 4; ++s) {
+    const StageD &d = h->d[s];
+    const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
+    const SB b = sb_at(h, h->seq_arena, lay[s], s, B, 0);
+    LEOD_TRY(front_fwd(h, s, (int64_t)B * L, s == 0 ? x : h_all[s - 1], x_dtype, x_h, x_w, b, st));
+    // input half of the gates for every timestep: gates = x2 W_x^T + bias
+    LEOD_TRY(gemm_nt(h, mk(b.x2[1], (int)C, h->w[s].Wl, (int)(2 * C), b.gates, (int)(4 * C), (int)(M * L), (int)(4 * C), (int)C,
+                           h->params + h->p[s].lstmb), st));
+    char *hs = (char *)h_all[s];
+    char *cs = (char *)h->seq_arena + lay[s].c_all * e;
+    for (int t = 0; t < L; ++t) {
       const void *hp = t == 0 ? (h0 ? h0[s] : nullptr) : hs + (t - 1) * M * C * e;
       const void *cp = t == 0 ? (c0 ? c0[s] : nullptr) : cs + (t - 1) * M * C * e;
-      if (s > 0) LEOD_TRY(front_fwd(h, s, B, (char *)h_all[s - 1] + (int64_t)t * B * d.Hi * d.Wi * d.Cin * e, 0, 0, 0, b, st));
-      LEOD_TRY(lstm_fwd(h, s, (int)M, b.x2[1], hp, cp, b.gates, hs + t * M * C * e, cs + t * M * C * e, st));
+      void *gt = (char *)b.gates + t * M * 4 * C * e;
+      if (hp)  // gates_t += h_{t-1} W_h^T (in place: every element is read and written by the same thread)
+        LEOD_TRY(gemm_nt(h, mk(hp, (int)C, eoff(h, h->w[s].Wl, C), (int)(2 * C), gt, (int)(4 * C), (int)M, (int)(4 * C), (int)C, nullptr,
+                               EPI_RESID, gt, (int)(4 * C)), st));
+      LEOD_TRY(lstm_pointwise_fwd(h->cfg.dtype, gt, cp, hs + t * M * C * e, cs + t * M * C * e, (int)M, (int)C, st));
     }
   }
   for (int s = 0; s < 4; ++s) {
@@ -725,34 +733,34 @@ extern "C" int leod_backbone_seq_bwd(leod_backbone_t *h, const void *x, int x_dt
   int64_t n;
   compute_layout(h, B, L, true, true, lay, &n);
   const int64_t e = (int64_t)h->esz();
-  for (int t = L - 1; t >= 0; --t) {
-    bool have_hint = false;
-    for (int s = 3; s >= 0; --s) {
-      const StageD &d = h->d[s];
-      const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
-      const SB b = sb_at(h, h->seq_arena, lay[s], s, B, t);
-      const GB g = gb_at(h, h->seq_arena, lay[s], s, B, t);
-      const char *cs = (const char *)h->seq_arena + lay[s].c_all * e;
+  // Stage-major, mirroring the forward: per stage the ConvLSTM recurrence runs backwards over time (gate math +
+  // dh_{t-1} = dgates_t W_h), then every other input-gradient kernel is batched over the L*B frames.
+  for (int s = 3; s >= 0; --s) {
+    const StageD &d = h->d[s];
+    const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
+    const StageW &w = h->w[s];
+    const SB b = sb_at(h, h->seq_arena, lay[s], s, B, 0);
+    const GB g = gb_at(h, h->seq_arena, lay[s], s, B, 0);
+    const char *cs = (const char *)h->seq_arena + lay[s].c_all * e;
+    const bool have_hint = s < 3;   // ws_hint = d loss / d h_all[s] from stage s+1's downsample, all timesteps
+    for (int t = L - 1; t >= 0; --t) {
       const void *cp = t == 0 ? (c0 ? c0[s] : nullptr) : cs + (t - 1) * M * C * e;
       const void *dh_head = (dh_all && dh_all[s]) ? (const char *)dh_all[s] + t * M * C * e : nullptr;
+      const void *dh_hint = have_hint ? (const char *)h->ws_hint + t * M * C * e : nullptr;
       const void *dh_next = t < L - 1 ? h->ws_dhc[s] : nullptr;            // from timestep t+1
       const void *dc_in = t < L - 1 ? h->ws_dcc[s] : (dc_last ? dc_last[s] : nullptr);
       const bool has_hp = t > 0 || (h0 && h0[s]);
       void *dc_out_ptr = (t == 0 && dc0 && dc0[s]) ? dc0[s] : h->ws_dcc[s];
       void *dh_out_ptr = !has_hp ? nullptr : ((t == 0) ? ((dh0 && dh0[s]) ? dh0[s] : nullptr) : h->ws_dhc[s]);
-      LEOD_TRY(lstm_bwd(h, s, (int)M, b.gates, cp, cs + t * M * C * e, dh_head, have_hint ? h->ws_hint : nullptr, dh_next, dc_in, g,
-                        dc_out_ptr, dh_out_ptr, st));
-      if (s > 0) {
-        LEOD_TRY(front_bwd(h, s, B, b, g, h->ws_hint, st));
-        have_hint = true;
-      }
+      void *dgt = (char *)g.dgates + t * M * 4 * C * e;
+      LEOD_TRY(lstm_pointwise_bwd(h->cfg.dtype, (const char *)b.gates + t * M * 4 * C * e, cp, cs + t * M * C * e, dh_head, dh_hint, dc_in,
+                                  dgt, dc_out_ptr, (int)M, (int)C, st, dh_next));
+      if (dh_out_ptr)
+        LEOD_TRY(gemm_nt(h, mk(dgt, (int)(4 * C), eoff(h, w.WlT, C * 4 * C), (int)(4 * C), dh_out_ptr, (int)C, (int)M, (int)C, (int)(4 * C)), st));
     }
-  }
-  // stage 1 blocks + stem for the whole window at once
-  {
-    const SB b = sb_at(h, h->seq_arena, lay[0], 0, B, 0);
-    const GB g = gb_at(h, h->seq_arena, lay[0], 0, B, 0);
-    LEOD_TRY(front_bwd(h, 0, (int64_t)B * L, b, g, nullptr, st));
+    // d loss / d x2 for all timesteps, then the two blocks and the downsample
+    LEOD_TRY(gemm_nt(h, mk(g.dgates, (int)(4 * C), w.WlT, (int)(4 * C), g.dy2[1], (int)C, (int)(M * L), (int)C, (int)(4 * C)), st));
+    LEOD_TRY(front_bwd(h, s, (int64_t)B * L, b, g, s > 0 ? h->ws_hint : nullptr, st));
   }
   // weight gradients: one GEMM per layer over all L timesteps
   for (int s = 0; s < 4; ++s) {

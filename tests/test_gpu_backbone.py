@@ -119,9 +119,11 @@ def test_backbone_gradients_smooth_loss_vs_oracle(net, dtype, impl):
 
 @pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
 def test_sequence_kernel_equals_per_step_calls(net, dtype):
-    """forward_sequence (one library call per BPTT window, stage 1 batched over time, deferred weight gradients)
-    against L calls of the per-timestep interface: same features, same final states, same parameter and
-    initial-state gradients — also when the window starts from a carried state."""
+    """forward_sequence (one library call per BPTT window, stage-major schedule: everything but the hidden-state half
+    of the ConvLSTM batched over time, deferred weight gradients) against L calls of the per-timestep interface: same
+    features, same final states, same parameter and initial-state gradients — also when the window starts from a
+    carried state.  bf16: the sequence path rounds the input half of the gates to bf16 before adding the hidden half
+    (one extra rounding per gate), hence the looser bound."""
     z, cfg, sd, d = net
     m = build(cfg, sd, (d['H'], d['W']), dtype).train()
     bb = m.backbone
@@ -157,16 +159,16 @@ def test_sequence_kernel_equals_per_step_calls(net, dtype):
             results.append(dict(feats={k: v.detach().float().clone() for k, v in feats.items()},
                                 c=[c.detach().float().clone() for _, c in states], grads=bb.flat_grads.clone(),
                                 dinit=None if start is None else [t.grad.float().clone() for hc in start for t in hc]))
-    tol = 1e-5 if dtype == 'fp32' else 2e-3
+    tol = 1e-5 if dtype == 'fp32' else 3e-2
     for a, b in ((results[0], results[2]), (results[1], results[3])):
         for k in a['feats']:
             assert rel_err(b['feats'][k], a['feats'][k]) < tol, k
         for ca, cb in zip(a['c'], b['c']):
             assert rel_err(cb, ca) < tol
-        assert rel_err(b['grads'], a['grads']) < (1e-4 if dtype == 'fp32' else 1e-2)
+        assert rel_err(b['grads'], a['grads']) < (1e-4 if dtype == 'fp32' else 5e-2)
         if a['dinit'] is not None:
             for ga, gb_ in zip(a['dinit'], b['dinit']):
-                assert rel_err(gb_, ga) < (1e-4 if dtype == 'fp32' else 1e-2)
+                assert rel_err(gb_, ga) < (1e-4 if dtype == 'fp32' else 5e-2)
 
 
 def test_training_step_module_sequence_vs_per_step(net):
