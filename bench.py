@@ -162,6 +162,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-kinds', action='store_true', help='print the per-kernel-class breakdown to stderr')
     ap.add_argument('--profile-csv', default=None, help='write one line per launch of the roofline pass to this CSV')
+    ap.add_argument('--no-graph-head', action='store_true', help='run neck/head/loss eagerly instead of replaying a CUDA graph')
     ap.add_argument('--phases', action='store_true', help='after the timed regions, time the phases of 3 extra steps (stderr)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -189,6 +190,8 @@ def main():
         module.mdl.fpn = torch.nn.SyncBatchNorm.convert_sync_batchnorm(module.mdl.fpn)
         module.mdl.yolox_head = torch.nn.SyncBatchNorm.convert_sync_batchnorm(module.mdl.yolox_head)
     module.to(dev).train()
+    # neck + head + loss fwd/bwd as one CUDA-graph replay (SyncBatchNorm collectives stay eager for N > 1)
+    module.mdl.graph_detect = (world == 1) and not args.no_graph_head
     bb = module.mdl.backbone
     if args.gemm_impl is not None:
         bb.set_gemm_impl(args.gemm_impl)

@@ -476,8 +476,48 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
   }
 }
 
-// column sums of a bf16 matrix into fp32 (bias gradients)
-__global__ void colsum_bf16_kernel(const bf16 *__restrict__ Y, int ldy, float *__restrict__ out, int M, int N, int rows_per_block) {
+// column sums of a bf16 matrix into fp32 (bias gradients).  Every thread owns one 8-column chunk (one 16-byte load per
+// row) and walks down the rows with a stride chosen so that a warp reads consecutive chunks: fully coalesced, 4 loads
+// in flight per thread.  blockDim.x is a multiple of the chunks per row, so the chunk of a thread never changes.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16 *__restrict__ Y, int ldy, float *__restrict__ out, int M, int N) {
+  __shared__ float red[256][9];
+  const int nc = N >> 3;
+  const int tid = threadIdx.x;
+  const int chunk = tid % nc;
+  const int rows_per_pass = blockDim.x / nc;
+  const int64_t row_stride = (int64_t)gridDim.x * rows_per_pass;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const bf16 *base = Y + (size_t)chunk * 8;
+  int64_t m = (int64_t)blockIdx.x * rows_per_pass + tid / nc;
+  for (; m + 3 * row_stride < M; m += 4 * row_stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4 *>(base + (size_t)(m + u * row_stride) * ldy);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bf16 *e = reinterpret_cast<const bf16 *>(&v[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(e[j]);
+    }
+  }
+  for (; m < M; m += row_stride) {
+    const uint4 v = *reinterpret_cast<const uint4 *>(base + (size_t)m * ldy);
+    const bf16 *e = reinterpret_cast<const bf16 *>(&v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(e[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[tid][j] = acc[j];
+  __syncthreads();
+  for (int i = tid; i < nc * 8; i += blockDim.x) {
+    const int c = i >> 3, j = i & 7;
+    float t = 0.f;
+    for (int r = 0; r < rows_per_pass; ++r) t += red[r * nc + c][j];
+    atomicAdd(&out[c * 8 + j], t);
+  }
+}
+// generic fallback (N not a multiple of 8 or more than 256 chunks per row)
+__global__ void colsum_bf16_slow_kernel(const bf16 *__restrict__ Y, int ldy, float *__restrict__ out, int M, int N, int rows_per_block) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
@@ -563,9 +603,17 @@ int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int l
   gemm_tn_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(mY, mX, a);
   LEOD_LAUNCH_CHECK();
   if (dbias) {
-    const int rpb = (int)round_up(ceil_div(M, 148 * 2), 32);
-    dim3 g2(ceil_div(N, 128), ceil_div(M, rpb));
-    colsum_bf16_kernel<<<g2, 128, 0, st>>>((const bf16 *)dY, ldy, dbias, M, N, rpb);
+    const int nc = N / 8;
+    if (N % 8 == 0 && nc <= 256) {
+      const int threads = 256 / nc * nc, rows_per_pass = threads / nc;
+      int blocks = ceil_div(M, rows_per_pass * 4);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      colsum_bf16_kernel<<<blocks, threads, 0, st>>>((const bf16 *)dY, ldy, dbias, M, N);
+    } else {
+      const int rpb = (int)round_up(ceil_div(M, 148 * 2), 32);
+      dim3 g2(ceil_div(N, 128), ceil_div(M, rpb));
+      colsum_bf16_slow_kernel<<<g2, 128, 0, st>>>((const bf16 *)dY, ldy, dbias, M, N, rpb);
+    }
     LEOD_LAUNCH_CHECK();
   }
   return 0;

@@ -174,8 +174,9 @@ class YOLOXHead(nn.Module):
         # IoU loss (losses.py:18-44), mean over foreground anchors
         tl = torch.max(box[..., :2] - box[..., 2:] / 2, reg_t[..., :2] - reg_t[..., 2:] / 2)
         br = torch.min(box[..., :2] + box[..., 2:] / 2, reg_t[..., :2] + reg_t[..., 2:] / 2)
-        en = (tl < br).to(tl.dtype).prod(-1)
-        inter = (br - tl).prod(-1) * en
+        en = ((tl[..., 0] < br[..., 0]) & (tl[..., 1] < br[..., 1])).to(tl.dtype)
+        d = br - tl                      # explicit product: prod()'s backward reads a zero-check back to the host
+        inter = d[..., 0] * d[..., 1] * en
         union = box[..., 2] * box[..., 3] + reg_t[..., 2] * reg_t[..., 3] - inter
         iou = inter / (union + 1e-16)
         loss_iou = (torch.where(fg, 1 - iou ** 2, torch.zeros_like(iou))).sum() / num_fg   # == mean over fg; 0 if none
