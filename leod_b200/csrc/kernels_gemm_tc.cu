@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -121,30 +122,182 @@ struct NtArgs {
   int BN;         // N tile (multiple of 16, <= 256)
   int stages;     // smem ring depth
   int nkb1, nkb;  // k-blocks of source 1 / total
-  int tmem_cols;  // power of two >= max(32, BN)
+  int tiles_m, tiles_n;
+  int acc_cols;   // TMEM columns per accumulator buffer (BN rounded up to 32)
+  int tmem_cols;  // power of two >= 2 * acc_cols
+  int staged;     // epilogue writes through shared memory (N multiple of 16: every chunk is full)
 };
 
-__global__ void __launch_bounds__(NUM_THREADS) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                 const __grid_constant__ CUtensorMap mapA2,
-                                                                 const __grid_constant__ CUtensorMap mapB,
-                                                                 const __grid_constant__ CUtensorMap mapB2, const NtArgs a) {
+constexpr int NT_EPI_WARPS = 8;
+constexpr int NT_THREADS = 64 + 32 * NT_EPI_WARPS;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// One 16-column chunk of one accumulator row: bias, fused epilogue, 2 x 16-byte stores.
+__device__ __forceinline__ void nt_epilogue_chunk(const GemmNT &g, const uint32_t (&r)[16], int m, int n) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  const int nvalid = min(16, g.N - n);
+  if (g.bias) {
+    if (nvalid == 16) {
+      const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + n);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b = __ldg(b4 + q);
+        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < nvalid) v[j] += g.bias[n + j];
+    }
+  }
+  if (nvalid == 16) {
+    if (g.epi == EPI_GELU) {
+      bf16 *ax = (bf16 *)g.aux + (size_t)m * g.ldaux + n;
+      __align__(16) bf16 t[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        t[j] = __float2bfloat16_rn(v[j]);
+        v[j] = gelu_f(v[j]);
+      }
+      ((uint4 *)ax)[0] = ((uint4 *)t)[0];
+      ((uint4 *)ax)[1] = ((uint4 *)t)[1];
+    } else if (g.epi == EPI_RESID) {
+      const bf16 *rx = (const bf16 *)g.R + (size_t)m * g.ldr + n;
+      __align__(16) bf16 t[16];
+      ((uint4 *)t)[0] = ((const uint4 *)rx)[0];
+      ((uint4 *)t)[1] = ((const uint4 *)rx)[1];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(t[j]);
+    } else if (g.epi == EPI_GELU_BWD) {
+      const bf16 *ax = (const bf16 *)g.aux + (size_t)m * g.ldaux + n;
+      __align__(16) bf16 t[16];
+      ((uint4 *)t)[0] = ((const uint4 *)ax)[0];
+      ((uint4 *)t)[1] = ((const uint4 *)ax)[1];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= gelu_grad_f(__bfloat162float(t[j]));
+    }
+    __align__(16) bf16 o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    bf16 *cx = (bf16 *)g.C + (size_t)m * g.ldc + n;
+    ((uint4 *)cx)[0] = ((uint4 *)o)[0];
+    ((uint4 *)cx)[1] = ((uint4 *)o)[1];
+  } else {
+    for (int j = 0; j < nvalid; ++j) {
+      float x = v[j];
+      if (g.epi == EPI_GELU) {
+        ((bf16 *)g.aux)[(size_t)m * g.ldaux + n + j] = __float2bfloat16_rn(x);
+        x = gelu_f(x);
+      } else if (g.epi == EPI_RESID) {
+        x += __bfloat162float(((const bf16 *)g.R)[(size_t)m * g.ldr + n + j]);
+      } else if (g.epi == EPI_GELU_BWD) {
+        x *= gelu_grad_f(__bfloat162float(((const bf16 *)g.aux)[(size_t)m * g.ldaux + n + j]));
+      }
+      ((bf16 *)g.C)[(size_t)m * g.ldc + n + j] = __float2bfloat16_rn(x);
+    }
+  }
+}
+
+// Same arithmetic for a full 16-column chunk, but the results stay in registers (packed bf16) so the caller can
+// stage them in shared memory and write whole 128-byte lines: o = output chunk, t = pre-GELU chunk (EPI_GELU only).
+__device__ __forceinline__ void nt_epilogue_compute(const GemmNT &g, const uint32_t (&r)[16], int m, int n, bool row_ok,
+                                                    uint4 (&o)[2], uint4 (&t)[2]) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  if (g.bias) {
+    const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = __ldg(b4 + q);
+      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+    }
+  }
+  if (g.epi == EPI_GELU) {
+    __align__(16) bf16 tt[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      tt[j] = __float2bfloat16_rn(v[j]);
+      v[j] = gelu_f(v[j]);
+    }
+    t[0] = ((uint4 *)tt)[0];
+    t[1] = ((uint4 *)tt)[1];
+  } else if (g.epi == EPI_RESID) {
+    if (row_ok) {
+      const bf16 *rx = (const bf16 *)g.R + (size_t)m * g.ldr + n;
+      __align__(16) bf16 tt[16];
+      ((uint4 *)tt)[0] = ((const uint4 *)rx)[0];
+      ((uint4 *)tt)[1] = ((const uint4 *)rx)[1];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(tt[j]);
+    }
+  } else if (g.epi == EPI_GELU_BWD) {
+    if (row_ok) {
+      const bf16 *ax = (const bf16 *)g.aux + (size_t)m * g.ldaux + n;
+      __align__(16) bf16 tt[16];
+      ((uint4 *)tt)[0] = ((const uint4 *)ax)[0];
+      ((uint4 *)tt)[1] = ((const uint4 *)ax)[1];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] *= gelu_grad_f(__bfloat162float(tt[j]));
+    }
+  }
+  __align__(16) bf16 oo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) oo[j] = __float2bfloat16_rn(v[j]);
+  o[0] = ((uint4 *)oo)[0];
+  o[1] = ((uint4 *)oo)[1];
+}
+
+// Write a staged [32 rows x 16*gc columns] bf16 block of one warp to global memory, 128 contiguous bytes per 8 lanes.
+// Staging layout: row pitch 128 B, 16-byte chunk c of row r at physical chunk c ^ (r & 7).
+__device__ __forceinline__ void nt_flush_stage(const uint8_t *stage, bf16 *dst, int ld, int m_base, int M, int n_base, int gc,
+                                               int lane) {
+  const int cpr = 2 * gc;              // 16-byte chunks per row
+  const int total = 32 * cpr;
+  for (int q = lane; q < total; q += 32) {
+    const int row = q / cpr, c = q - row * cpr;
+    if (m_base + row < M) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(stage + row * 128 + ((c ^ (row & 7)) << 4));
+      *reinterpret_cast<uint4 *>(dst + (size_t)(m_base + row) * ld + n_base + c * 8) = v;
+    }
+  }
+}
+
+// Persistent: every CTA walks the tile list with stride gridDim.x (n-tile fastest, so CTAs running side by side share
+// an A tile through L2).  The TMA ring runs ahead across tile boundaries, the accumulator is double-buffered in TMEM
+// so the MMAs of tile j+1 overlap the epilogue of tile j, and eight epilogue warps (two per TMEM lane quarter, each
+// taking half of the columns) drain it.
+__global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                    const __grid_constant__ CUtensorMap mapA2,
+                                                                    const __grid_constant__ CUtensorMap mapB,
+                                                                    const __grid_constant__ CUtensorMap mapB2, const NtArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = a.BN * TILE_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint64_t *bars = (uint64_t *)(smem + (size_t)a.stages * stage_bytes);
-  uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages;
-  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * a.stages + 1);
+  uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages, *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 2);
+  // per epilogue warp: two 4 KB staging blocks (32 rows x 64 columns bf16), 128-byte aligned
+  uint8_t *stage_base = (uint8_t *)(((uintptr_t)(tmem_slot + 4) + 127) & ~(uintptr_t)127);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * a.BN, m0 = blockIdx.y * TILE_M;
+  const int num_tiles = a.tiles_m * a.tiles_n;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    mbar_init(smem_u32(tmem_full), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_empty[b]), NT_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -159,119 +312,118 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_nt_tc_kernel(const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < a.nkb; ++kb) {
-        const int s = kb % a.stages;
-        const uint32_t ph = (kb / a.stages) & 1;
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-        const uint32_t fb = smem_u32(&full_bar[s]);
-        mbar_expect_tx(fb, stage_bytes);
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
-        if (kb < a.nkb1) {
-          tma_load_2d(sa, &mapA, fb, kb * TILE_K, m0);
-          tma_load_2d(sb, &mapB, fb, kb * TILE_K, n0);
-        } else {
-          tma_load_2d(sa, &mapA2, fb, (kb - a.nkb1) * TILE_K, m0);
-          tma_load_2d(sb, &mapB2, fb, (kb - a.nkb1) * TILE_K, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / a.tiles_n) * TILE_M, n0 = (tile % a.tiles_n) * a.BN;
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[s]);
+          mbar_expect_tx(fb, stage_bytes);
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
+          if (kb < a.nkb1) {
+            tma_load_2d(sa, &mapA, fb, kb * TILE_K, m0);
+            tma_load_2d(sb, &mapB, fb, kb * TILE_K, n0);
+          } else {
+            tma_load_2d(sa, &mapA2, fb, (kb - a.nkb1) * TILE_K, m0);
+            tma_load_2d(sb, &mapB2, fb, (kb - a.nkb1) * TILE_K, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(TILE_M, a.BN, 0, 0);
-      for (int kb = 0; kb < a.nkb; ++kb) {
-        const int s = kb % a.stages;
-        const uint32_t ph = (kb / a.stages) & 1;
-        mbar_wait(smem_u32(&full_bar[s]), ph);
+      int it = 0, j = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+        const int buf = j & 1;
+        mbar_wait(smem_u32(&tmem_empty[buf]), ((j >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
-        const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
+        const uint32_t acc = tmem_base + (uint32_t)(buf * a.acc_cols);
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % a.stages;
+          const uint32_t ph = (it / a.stages) & 1;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
+          const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < TILE_K / 16; ++k) {
-          // +32 bytes per 16-element K step inside the 128B swizzle row (>>4 encoded: +2)
-          tc_mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < TILE_K / 16; ++k) {
+            // +32 bytes per 16-element K step inside the 128B swizzle row (>>4 encoded: +2)
+            tc_mma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          tc_commit(smem_u32(&empty_bar[s]));
         }
-        tc_commit(smem_u32(&empty_bar[s]));
+        tc_commit(smem_u32(&tmem_full[buf]));
       }
-      tc_commit(smem_u32(tmem_full));
     }
   } else {
-    // epilogue: TMEM lane quarter = warp % 4, one accumulator row per thread
-    const int quarter = warp & 3;
-    const int m = m0 + quarter * 32 + lane;
-    mbar_wait(smem_u32(tmem_full), 0);
-    tc_fence_after();
+    // epilogue: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4, one accumulator row per thread
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int nchunks = a.BN >> 4;
+    const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2, c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
     const GemmNT &g = a.g;
-    const bool row_ok = m < g.M;
-    const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t rbuf[2][16];
-    tmem_ld16_async(trow, rbuf[0]);
+    int j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const int m0 = (tile / a.tiles_n) * TILE_M, n0 = (tile % a.tiles_n) * a.BN;
+      const int buf = j & 1;
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < g.M;
+      mbar_wait(smem_u32(&tmem_full[buf]), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * a.acc_cols);
+      uint32_t rbuf[2][16];
+      if (c_begin < c_end) tmem_ld16_async(trow + (uint32_t)(c_begin * 16), rbuf[0]);
+      if (a.staged) {
+        uint8_t *stC = stage_base + (warp - 2) * 8192, *stT = stC + 4096;
+        const int m_base = m0 + quarter * 32;
+        int gs = c_begin;   // first chunk of the current group of <= 4 chunks
 #pragma unroll 1
-    for (int c = 0; c < a.BN; c += 32) {
+        for (int c = c_begin; c < c_end; c += 2) {
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-      const int cc = c + 16 * half;
-      if (cc >= a.BN) break;
-      tmem_ld_wait(rbuf[half]);
-      if (cc + 16 < a.BN) tmem_ld16_async(trow + (uint32_t)(cc + 16), rbuf[half ^ 1]);
-      const uint32_t (&r)[16] = rbuf[half];
-      const int n = n0 + cc;
-      if (!row_ok || n >= g.N) continue;
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-      const int nvalid = min(16, g.N - n);
-      if (g.bias) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nvalid) v[j] += g.bias[n + j];
-      }
-      if (nvalid == 16) {
-        if (g.epi == EPI_GELU) {
-          bf16 *ax = (bf16 *)g.aux + (size_t)m * g.ldaux + n;
-          __align__(16) bf16 t[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            t[j] = __float2bfloat16_rn(v[j]);
-            v[j] = gelu_f(v[j]);
+          for (int hh = 0; hh < 2; ++hh) {
+            const int cc = c + hh;
+            if (cc >= c_end) break;
+            tmem_ld_wait(rbuf[hh]);
+            if (cc + 1 < c_end) tmem_ld16_async(trow + (uint32_t)((cc + 1) * 16), rbuf[hh ^ 1]);
+            uint4 o[2], t[2];
+            nt_epilogue_compute(g, rbuf[hh], m, n0 + cc * 16, row_ok, o, t);
+            const int slot = (cc - gs) * 2, sw = lane & 7;
+            *reinterpret_cast<uint4 *>(stC + lane * 128 + (((slot) ^ sw) << 4)) = o[0];
+            *reinterpret_cast<uint4 *>(stC + lane * 128 + (((slot + 1) ^ sw) << 4)) = o[1];
+            if (g.epi == EPI_GELU) {
+              *reinterpret_cast<uint4 *>(stT + lane * 128 + (((slot) ^ sw) << 4)) = t[0];
+              *reinterpret_cast<uint4 *>(stT + lane * 128 + (((slot + 1) ^ sw) << 4)) = t[1];
+            }
+            if (cc - gs == 3 || cc == c_end - 1) {
+              __syncwarp();
+              const int gc = cc - gs + 1;
+              nt_flush_stage(stC, (bf16 *)g.C, g.ldc, m_base, g.M, n0 + gs * 16, gc, lane);
+              if (g.epi == EPI_GELU) nt_flush_stage(stT, (bf16 *)g.aux, g.ldaux, m_base, g.M, n0 + gs * 16, gc, lane);
+              __syncwarp();
+              gs = cc + 1;
+            }
           }
-          ((uint4 *)ax)[0] = ((uint4 *)t)[0];
-          ((uint4 *)ax)[1] = ((uint4 *)t)[1];
-        } else if (g.epi == EPI_RESID) {
-          const bf16 *rx = (const bf16 *)g.R + (size_t)m * g.ldr + n;
-          __align__(16) bf16 t[16];
-          ((uint4 *)t)[0] = ((const uint4 *)rx)[0];
-          ((uint4 *)t)[1] = ((const uint4 *)rx)[1];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(t[j]);
-        } else if (g.epi == EPI_GELU_BWD) {
-          const bf16 *ax = (const bf16 *)g.aux + (size_t)m * g.ldaux + n;
-          __align__(16) bf16 t[16];
-          ((uint4 *)t)[0] = ((const uint4 *)ax)[0];
-          ((uint4 *)t)[1] = ((const uint4 *)ax)[1];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= gelu_grad_f(__bfloat162float(t[j]));
         }
-        __align__(16) bf16 o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = __float2bfloat16_rn(v[j]);
-        bf16 *cx = (bf16 *)g.C + (size_t)m * g.ldc + n;
-        ((uint4 *)cx)[0] = ((uint4 *)o)[0];
-        ((uint4 *)cx)[1] = ((uint4 *)o)[1];
       } else {
-        for (int j = 0; j < nvalid; ++j) {
-          float x = v[j];
-          if (g.epi == EPI_GELU) {
-            ((bf16 *)g.aux)[(size_t)m * g.ldaux + n + j] = __float2bfloat16_rn(x);
-            x = gelu_f(x);
-          } else if (g.epi == EPI_RESID) {
-            x += __bfloat162float(((const bf16 *)g.R)[(size_t)m * g.ldr + n + j]);
-          } else if (g.epi == EPI_GELU_BWD) {
-            x *= gelu_grad_f(__bfloat162float(((const bf16 *)g.aux)[(size_t)m * g.ldaux + n + j]));
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 2) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int cc = c + hh;
+            if (cc >= c_end) break;
+            tmem_ld_wait(rbuf[hh]);
+            if (cc + 1 < c_end) tmem_ld16_async(trow + (uint32_t)((cc + 1) * 16), rbuf[hh ^ 1]);
+            const int n = n0 + cc * 16;
+            if (row_ok && n < g.N) nt_epilogue_chunk(g, rbuf[hh], m, n);
           }
-          ((bf16 *)g.C)[(size_t)m * g.ldc + n + j] = __float2bfloat16_rn(x);
         }
       }
-    }
+      // all tcgen05.ld of this warp have completed (wait::ld above): hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
     }
   }
   tc_fence_before();
@@ -340,11 +492,11 @@ int make_map(CUtensorMap *out, const void *ptr, uint64_t inner, uint64_t outer, 
   return 0;
 }
 
-// N tile: as wide as possible (A is read once per N tile) but (a) small-K tiles are latency bound, so
-// keep the TMEM allocation <= 128 columns there (4 CTAs per SM), and (b) small-M problems need enough
-// CTAs to cover the 148 SMs, so narrow the tile until the grid has >= ~120 CTAs.
+// N tile: as wide as possible (A is then read once and B stays L2-resident), but small-M problems need enough tiles to
+// cover the 148 SMs, so narrow the tile until there are >= ~120 of them.
 int pick_bn(int M, int N, int K) {
-  const int cap = K <= 128 ? 128 : 256;
+  const int cap = 256;
+  (void)K;
   const int tiles_m = ceil_div(M, TILE_M);
   int best = 0;
   for (int bn = cap; bn >= 32; bn -= 16) {
@@ -527,6 +679,15 @@ __global__ void colsum_bf16_slow_kernel(const bf16 *__restrict__ Y, int ldy, flo
 }
 }  // namespace
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
   LEOD_REQUIRE(g.K > 0, "gemm_nt_tc: K = %d", g.K);
@@ -540,9 +701,16 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   LEOD_REQUIRE(K1 > 0 && K2 >= 0 && (K2 == 0 || K1 % 8 == 0), "gemm_nt_tc: bad K split %d/%d", K1, g.K);
   a.nkb1 = ceil_div(K1, TILE_K);
   a.nkb = a.nkb1 + (K2 > 0 ? ceil_div(K2, TILE_K) : 0);
-  a.stages = a.nkb < 4 ? a.nkb : 4;
+  a.tiles_m = ceil_div(g.M, TILE_M);
+  a.tiles_n = ceil_div(g.N, a.BN);
+  a.acc_cols = (int)round_up(a.BN, 32);
   a.tmem_cols = 32;
-  while (a.tmem_cols < a.BN) a.tmem_cols *= 2;
+  while (a.tmem_cols < 2 * a.acc_cols) a.tmem_cols *= 2;
+  const int stage_bytes = A_STAGE_BYTES + a.BN * TILE_K * 2;
+  const int total_kb = a.nkb * ceil_div(a.tiles_m * a.tiles_n, num_sms());
+  a.staged = (g.N % 16 == 0 && (((uintptr_t)g.bias) & 15) == 0) ? 1 : 0;
+  const int epi_bytes = NT_EPI_WARPS * 8192 + 256;
+  a.stages = std::min(std::min(4, (int)((224 * 1024 - epi_bytes - 2048) / stage_bytes)), std::max(total_kb, 1));
   CUtensorMap mA, mA2, mB, mB2;
   LEOD_TRY(make_map(&mA, g.A, K1, g.M, g.lda, TILE_K, TILE_M));
   LEOD_TRY(make_map(&mB, g.B, K1, g.N, g.ldb, TILE_K, a.BN));
@@ -553,15 +721,17 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
     mA2 = mA;
     mB2 = mB;
   }
-  const int stage_bytes = A_STAGE_BYTES + a.BN * TILE_K * 2;
-  const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + (2 * a.stages + 2) * 8;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    smem_set = 200 * 1024;
+  const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + (2 * a.stages + 4) * 8 + 16 + epi_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    attr_set = true;
   }
-  dim3 grid(ceil_div(g.N, a.BN), ceil_div(g.M, TILE_M));
-  gemm_nt_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+  // balanced persistent grid: the smallest CTA count that still finishes in the minimal number of waves
+  const int tiles = a.tiles_m * a.tiles_n;
+  const int waves = ceil_div(tiles, num_sms());
+  const int grid = ceil_div(tiles, waves);
+  gemm_nt_tc_kernel<<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
