@@ -203,8 +203,35 @@ __device__ __forceinline__ void nt_epilogue_chunk(const GemmNT &g, const uint32_
   }
 }
 
+// erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution) on the MUFU rcp / ex2 units: about a
+// third of the instructions of erff().  e = exp(-x^2/2) is shared between GELU and its derivative.
+__device__ __forceinline__ void gelu_parts_fast(float x, float &cdf, float &e) {
+  const float ax = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
+  const float h = 0.5f * p * e;               // 0.5 * (1 - erf(|x|/sqrt2))
+  cdf = x >= 0.f ? 1.0f - h : h;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, e;
+  gelu_parts_fast(x, cdf, e);
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float cdf, e;
+  gelu_parts_fast(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+
 // Same arithmetic for a full 16-column chunk, but the results stay in registers (packed bf16) so the caller can
 // stage them in shared memory and write whole 128-byte lines: o = output chunk, t = pre-GELU chunk (EPI_GELU only).
+template <int EPI>
 __device__ __forceinline__ void nt_epilogue_compute(const GemmNT &g, const uint32_t (&r)[16], int m, int n, bool row_ok,
                                                     uint4 (&o)[2], uint4 (&t)[2]) {
   float v[16];
@@ -218,53 +245,69 @@ __device__ __forceinline__ void nt_epilogue_compute(const GemmNT &g, const uint3
       v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
     }
   }
-  if (g.epi == EPI_GELU) {
-    __align__(16) bf16 tt[16];
+  if (EPI == EPI_GELU) {
+    uint32_t *tw = reinterpret_cast<uint32_t *>(t);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      tt[j] = __float2bfloat16_rn(v[j]);
-      v[j] = gelu_f(v[j]);
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat162 pr = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      tw[j] = *reinterpret_cast<const uint32_t *>(&pr);
+      v[2 * j] = gelu_fast(v[2 * j]);
+      v[2 * j + 1] = gelu_fast(v[2 * j + 1]);
     }
-    t[0] = ((uint4 *)tt)[0];
-    t[1] = ((uint4 *)tt)[1];
-  } else if (g.epi == EPI_RESID) {
+  } else if (EPI == EPI_RESID) {
     if (row_ok) {
-      const bf16 *rx = (const bf16 *)g.R + (size_t)m * g.ldr + n;
-      __align__(16) bf16 tt[16];
-      ((uint4 *)tt)[0] = ((const uint4 *)rx)[0];
-      ((uint4 *)tt)[1] = ((const uint4 *)rx)[1];
+      const uint4 *rx = reinterpret_cast<const uint4 *>((const bf16 *)g.R + (size_t)m * g.ldr + n);
+      const uint4 r0 = rx[0], r1 = rx[1];
+      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(tt[j]);
+      for (int j = 0; j < 8; ++j) {   // bf16 -> fp32 is a 16-bit shift
+        v[2 * j] += __uint_as_float(w[j] << 16);
+        v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+      }
     }
-  } else if (g.epi == EPI_GELU_BWD) {
+  } else if (EPI == EPI_GELU_BWD) {
     if (row_ok) {
-      const bf16 *ax = (const bf16 *)g.aux + (size_t)m * g.ldaux + n;
-      __align__(16) bf16 tt[16];
-      ((uint4 *)tt)[0] = ((const uint4 *)ax)[0];
-      ((uint4 *)tt)[1] = ((const uint4 *)ax)[1];
+      const uint4 *ax = reinterpret_cast<const uint4 *>((const bf16 *)g.aux + (size_t)m * g.ldaux + n);
+      const uint4 r0 = ax[0], r1 = ax[1];
+      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] *= gelu_grad_f(__bfloat162float(tt[j]));
+      for (int j = 0; j < 8; ++j) {
+        v[2 * j] *= gelu_grad_fast(__uint_as_float(w[j] << 16));
+        v[2 * j + 1] *= gelu_grad_fast(__uint_as_float(w[j] & 0xffff0000u));
+      }
     }
   }
-  __align__(16) bf16 oo[16];
+  uint32_t *ow = reinterpret_cast<uint32_t *>(o);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) oo[j] = __float2bfloat16_rn(v[j]);
-  o[0] = ((uint4 *)oo)[0];
-  o[1] = ((uint4 *)oo)[1];
+  for (int j = 0; j < 8; ++j) {
+    const __nv_bfloat162 pr = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    ow[j] = *reinterpret_cast<const uint32_t *>(&pr);
+  }
 }
 
-// Write a staged [32 rows x 16*gc columns] bf16 block of one warp to global memory, 128 contiguous bytes per 8 lanes.
+// Write a staged [32 rows x 16*GC columns] bf16 block of one warp to global memory, 128 contiguous bytes per 8 lanes.
 // Staging layout: row pitch 128 B, 16-byte chunk c of row r at physical chunk c ^ (r & 7).
-__device__ __forceinline__ void nt_flush_stage(const uint8_t *stage, bf16 *dst, int ld, int m_base, int M, int n_base, int gc,
-                                               int lane) {
-  const int cpr = 2 * gc;              // 16-byte chunks per row
-  const int total = 32 * cpr;
-  for (int q = lane; q < total; q += 32) {
-    const int row = q / cpr, c = q - row * cpr;
-    if (m_base + row < M) {
+template <int GC>
+__device__ __forceinline__ void nt_flush_stage_n(const uint8_t *stage, bf16 *dst, int ld, int m_base, int rows_ok, int n_base, int lane) {
+  constexpr int CPR = 2 * GC;          // 16-byte chunks per row
+#pragma unroll
+  for (int it = 0; it < CPR; ++it) {
+    const int q = lane + 32 * it;
+    const int row = q / CPR, c = q % CPR;
+    if (row < rows_ok) {
       const uint4 v = *reinterpret_cast<const uint4 *>(stage + row * 128 + ((c ^ (row & 7)) << 4));
       *reinterpret_cast<uint4 *>(dst + (size_t)(m_base + row) * ld + n_base + c * 8) = v;
     }
+  }
+}
+__device__ __forceinline__ void nt_flush_stage(const uint8_t *stage, bf16 *dst, int ld, int m_base, int M, int n_base, int gc,
+                                               int lane) {
+  const int rows_ok = min(32, M - m_base);
+  switch (gc) {
+    case 4: nt_flush_stage_n<4>(stage, dst, ld, m_base, rows_ok, n_base, lane); break;
+    case 3: nt_flush_stage_n<3>(stage, dst, ld, m_base, rows_ok, n_base, lane); break;
+    case 2: nt_flush_stage_n<2>(stage, dst, ld, m_base, rows_ok, n_base, lane); break;
+    default: nt_flush_stage_n<1>(stage, dst, ld, m_base, rows_ok, n_base, lane); break;
   }
 }
 
@@ -272,6 +315,7 @@ __device__ __forceinline__ void nt_flush_stage(const uint8_t *stage, bf16 *dst, 
 // an A tile through L2).  The TMA ring runs ahead across tile boundaries, the accumulator is double-buffered in TMEM
 // so the MMAs of tile j+1 overlap the epilogue of tile j, and eight epilogue warps (two per TMEM lane quarter, each
 // taking half of the columns) drain it.
+template <int EPI>   // EPI_* : staged epilogue specialised for that mode;  -1 : generic per-thread stores (ragged N)
 __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                     const __grid_constant__ CUtensorMap mapA2,
                                                                     const __grid_constant__ CUtensorMap mapB,
@@ -375,7 +419,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * a.acc_cols);
       uint32_t rbuf[2][16];
       if (c_begin < c_end) tmem_ld16_async(trow + (uint32_t)(c_begin * 16), rbuf[0]);
-      if (a.staged) {
+      if (EPI >= 0) {
         uint8_t *stC = stage_base + (warp - 2) * 8192, *stT = stC + 4096;
         const int m_base = m0 + quarter * 32;
         int gs = c_begin;   // first chunk of the current group of <= 4 chunks
@@ -388,11 +432,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc_kernel(const __grid_
             tmem_ld_wait(rbuf[hh]);
             if (cc + 1 < c_end) tmem_ld16_async(trow + (uint32_t)((cc + 1) * 16), rbuf[hh ^ 1]);
             uint4 o[2], t[2];
-            nt_epilogue_compute(g, rbuf[hh], m, n0 + cc * 16, row_ok, o, t);
+            nt_epilogue_compute<EPI>(g, rbuf[hh], m, n0 + cc * 16, row_ok, o, t);
             const int slot = (cc - gs) * 2, sw = lane & 7;
             *reinterpret_cast<uint4 *>(stC + lane * 128 + (((slot) ^ sw) << 4)) = o[0];
             *reinterpret_cast<uint4 *>(stC + lane * 128 + (((slot + 1) ^ sw) << 4)) = o[1];
-            if (g.epi == EPI_GELU) {
+            if (EPI == EPI_GELU) {
               *reinterpret_cast<uint4 *>(stT + lane * 128 + (((slot) ^ sw) << 4)) = t[0];
               *reinterpret_cast<uint4 *>(stT + lane * 128 + (((slot + 1) ^ sw) << 4)) = t[1];
             }
@@ -400,7 +444,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc_kernel(const __grid_
               __syncwarp();
               const int gc = cc - gs + 1;
               nt_flush_stage(stC, (bf16 *)g.C, g.ldc, m_base, g.M, n0 + gs * 16, gc, lane);
-              if (g.epi == EPI_GELU) nt_flush_stage(stT, (bf16 *)g.aux, g.ldaux, m_base, g.M, n0 + gs * 16, gc, lane);
+              if (EPI == EPI_GELU) nt_flush_stage(stT, (bf16 *)g.aux, g.ldaux, m_base, g.M, n0 + gs * 16, gc, lane);
               __syncwarp();
               gs = cc + 1;
             }
@@ -724,14 +768,28 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + (2 * a.stages + 4) * 8 + 16 + epi_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<EPI_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<EPI_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
+    LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<EPI_GELU_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));
     attr_set = true;
   }
   // balanced persistent grid: the smallest CTA count that still finishes in the minimal number of waves
   const int tiles = a.tiles_m * a.tiles_n;
   const int waves = ceil_div(tiles, num_sms());
   const int grid = ceil_div(tiles, waves);
-  gemm_nt_tc_kernel<<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+  if (!a.staged) {
+    gemm_nt_tc_kernel<-1><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+  } else if (g.epi == EPI_GELU) {
+    gemm_nt_tc_kernel<EPI_GELU><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+  } else if (g.epi == EPI_RESID) {
+    gemm_nt_tc_kernel<EPI_RESID><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+  } else if (g.epi == EPI_GELU_BWD) {
+    gemm_nt_tc_kernel<EPI_GELU_BWD><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+  } else {
+    gemm_nt_tc_kernel<EPI_NONE><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+  }
   LEOD_LAUNCH_CHECK();
   return 0;
 }
