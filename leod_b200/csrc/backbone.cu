@@ -76,6 +76,9 @@ struct leod_backbone {
   // sequence arena
   int seq_B = 0, seq_L = 0;
   void *seq_arena = nullptr;
+  void *seq_col0 = nullptr;      // stem patch matrix of the whole window [L*B*Ho*Wo, Kp] (kept from forward to backward)
+  int64_t seq_col0_imgs = 0;
+  bool col0_live = false;        // set for the duration of a sequence-mode forward/backward pair
   size_t esz() const { return cfg.dtype == LEOD_BF16 ? 2 : 4; }
   int gemm_impl = 0;  // 0 SIMT, 1 tensor core (bf16 only)
 };
@@ -135,6 +138,16 @@ __global__ void conv_grad_unpermute_kernel(float *__restrict__ G, float *__restr
   const int n = (int)(idx / K), k = (int)(idx % K);
   const int cin = k % Cin, kx = (k / Cin) % ksz, ky = k / (Cin * ksz);
   dW[(((size_t)n * Cin + cin) * ksz + ky) * ksz + kx] += G[idx];
+  G[idx] = 0.f;
+}
+// stem layout: k = (cin*ksz + ky)*8 + slot, slots 1..ksz <-> kx (kernels_elem.cu, im2col_nchw_kernel)
+__global__ void stem_grad_unpermute_kernel(float *__restrict__ G, float *__restrict__ dW, int N, int Cin, int ksz) {
+  const int K = Cin * ksz * 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * K) return;
+  const int n = (int)(idx / K), k = (int)(idx % K);
+  const int slot = k & 7, r = k >> 3;
+  if (slot >= 1 && slot <= ksz) dW[(size_t)n * Cin * ksz * ksz + (size_t)r * ksz + (slot - 1)] += G[idx];
   G[idx] = 0.f;
 }
 
@@ -271,17 +284,20 @@ int front_fwd(leod_backbone *h, int s, int64_t nimg, const void *in, int x_dtype
   const int64_t M64 = nimg * rows_per_img;
   LEOD_REQUIRE(M64 * std::max(4 * C, d.Kp) < (1LL << 31), "stage %d: %lld rows exceed the 32-bit indexing of the kernels", s, (long long)M64);
   const int M = (int)M64;
-  const int64_t chunk_imgs = std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
+  // the stem's patch matrix of a whole BPTT window is kept for the weight-gradient GEMM (seq_col0, sequence mode)
+  const bool keep = s == 0 && h->col0_live && h->seq_col0 && nimg == h->seq_col0_imgs;
+  const int64_t chunk_imgs = keep ? nimg : std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
   for (int64_t i0 = 0; i0 < nimg; i0 += chunk_imgs) {
     const int n = (int)std::min<int64_t>(chunk_imgs, nimg - i0);
+    void *colp = keep ? h->seq_col0 : h->ws_col;
     if (s == 0) {
       const char *xin = (const char *)in + i0 * d.Cin * x_h * x_w * (int64_t)dtype_size(x_dtype);
-      LEOD_TRY(im2col_nchw(x_dtype, dt, xin, h->ws_col, n, d.Cin, x_h, x_w, d.Hi, d.Wi, d.ksz, d.stride, d.pad, d.Kp, st));
+      LEOD_TRY(im2col_nchw(x_dtype, dt, xin, colp, n, d.Cin, x_h, x_w, d.Hi, d.Wi, d.ksz, d.stride, d.pad, d.Kp, st));
     } else {
       const char *xin = (const char *)in + i0 * d.Hi * d.Wi * d.Cin * e;
-      LEOD_TRY(im2col_nhwc(dt, xin, h->ws_col, n, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, d.Kp, st));
+      LEOD_TRY(im2col_nhwc(dt, xin, colp, n, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, d.Kp, st));
     }
-    LEOD_TRY(gemm_nt(h, mk(h->ws_col, d.Kp, w.Wconv, d.Kp, (char *)b.y0 + i0 * rows_per_img * C * e, C, (int)(n * rows_per_img), C, d.Kp), st));
+    LEOD_TRY(gemm_nt(h, mk(colp, d.Kp, w.Wconv, d.Kp, (char *)b.y0 + i0 * rows_per_img * C * e, C, (int)(n * rows_per_img), C, d.Kp), st));
   }
   LEOD_TRY(layernorm_fwd(dt, b.y0, P + p.lnw, P + p.lnb, b.x0, M, C, 1e-5f, st));
   const void *xin = b.x0;
@@ -393,18 +409,21 @@ int stage_wgrads(leod_backbone *h, int s, int64_t nimg, const void *in, int x_dt
     LEOD_TRY(gemm_tn(h, g.dy1[k], C, b.att[k], C, bw.Gproj, C, bw.sproj, M, C, C, st));
     LEOD_TRY(gemm_tn(h, g.dqkv[k], 3 * C, k == 1 ? b.xn1 : b.x0, C, G + q.qkvw, C, G + q.qkvb, M, 3 * C, C, st));
   }
-  const int64_t chunk_imgs = std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
+  const bool keep = s == 0 && h->col0_live && h->seq_col0 && nimg == h->seq_col0_imgs;   // patches still there from the forward pass
+  const int64_t chunk_imgs = keep ? nimg : std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
   for (int64_t i0 = 0; i0 < nimg; i0 += chunk_imgs) {
     const int n = (int)std::min<int64_t>(chunk_imgs, nimg - i0);
-    if (s == 0) {
+    void *colp = keep ? h->seq_col0 : h->ws_col;
+    if (keep) {
+    } else if (s == 0) {
       const char *xin = (const char *)in + i0 * d.Cin * x_h * x_w * (int64_t)dtype_size(x_dtype);
-      LEOD_TRY(im2col_nchw(x_dtype, dt, xin, h->ws_col, n, d.Cin, x_h, x_w, d.Hi, d.Wi, d.ksz, d.stride, d.pad, d.Kp, st));
+      LEOD_TRY(im2col_nchw(x_dtype, dt, xin, colp, n, d.Cin, x_h, x_w, d.Hi, d.Wi, d.ksz, d.stride, d.pad, d.Kp, st));
     } else {
       const char *xin = (const char *)in + i0 * d.Hi * d.Wi * d.Cin * e;
-      LEOD_TRY(im2col_nhwc(dt, xin, h->ws_col, n, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, d.Kp, st));
+      LEOD_TRY(im2col_nhwc(dt, xin, colp, n, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, d.Kp, st));
     }
-    // stage 0 patches are in the parameter's own (cin,ky,kx) order; later stages use (ky,kx,cin) -> scratch
-    LEOD_TRY(gemm_tn(h, (char *)g.dy0 + i0 * rows_per_img * C * e, C, h->ws_col, d.Kp, s == 0 ? G + p.convw : w.Gconv, d.K, nullptr,
+    // patch layouts differ from the parameter's (cin,ky,kx) order -> scratch, unpermuted by leod_backbone_grads_finalize
+    LEOD_TRY(gemm_tn(h, (char *)g.dy0 + i0 * rows_per_img * C * e, C, colp, d.Kp, w.Gconv, d.K, nullptr,
                      (int)(n * rows_per_img), C, d.K, st));
   }
   return 0;
@@ -443,7 +462,7 @@ static int backbone_create_impl(const leod_backbone_cfg *cfg, leod_backbone_t **
     d.pad = d.ksz / 2;
     d.Hi = Hi; d.Wi = Wi;
     d.Ho = Hi / d.stride; d.Wo = Wi / d.stride;
-    d.K = Cin * d.ksz * d.ksz;
+    d.K = s == 0 ? Cin * d.ksz * 8 : Cin * d.ksz * d.ksz;   // the stem pads every kernel row to 8 taps (im2col_nchw_kernel)
     d.Kp = (int)round_up(d.K, 8);
     Hi = d.Ho; Wi = d.Wo; Cin = d.C;
     const int64_t C = d.C, R = cfg->mlp_ratio;
@@ -529,6 +548,7 @@ extern "C" void leod_backbone_destroy(leod_backbone_t *h) {
   for (void *p : h->owned) cudaFree(p);
   free_workspace(h);
   if (h->seq_arena) cudaFree(h->seq_arena);
+  if (h->seq_col0) cudaFree(h->seq_col0);
   delete h;
 }
 
@@ -572,7 +592,7 @@ extern "C" int leod_backbone_prepare(leod_backbone_t *h, void *stream) {
     const int C = d.C, R = h->cfg.mlp_ratio;
     const StageP &p = h->p[s];
     StageW &w = h->w[s];
-    LEOD_TRY(prep_weight(dt, P + p.convw, nullptr, w.Wconv, d.Kp, w.WconvT, C, C, d.K, s == 0 ? 0 : 1, d.Cin, d.ksz, st));
+    LEOD_TRY(prep_weight(dt, P + p.convw, nullptr, w.Wconv, d.Kp, w.WconvT, C, C, d.K, s == 0 ? 2 : 1, d.Cin, d.ksz, st));
     for (int b = 0; b < 2; ++b) {
       const BlockP &q = p.blk[b];
       BlockW &bw = w.blk[b];
@@ -607,6 +627,7 @@ extern "C" int leod_backbone_step_fwd(leod_backbone_t *h, const void *x, int x_d
                                       void *const c_out[4], void *save, void *stream) {
   LEOD_TRY(check_common(h, x, x_h, x_w, B, "leod_backbone_step_fwd"));
   LEOD_REQUIRE(h_out && c_out, "leod_backbone_step_fwd: null output arrays");
+  h->col0_live = false;
   cudaStream_t st = (cudaStream_t)stream;
   LEOD_TRY(ensure_workspace(h, B, B));
   StageLayout lay[4];
@@ -630,6 +651,7 @@ extern "C" int leod_backbone_step_bwd(leod_backbone_t *h, const void *x, int x_d
   LEOD_TRY(check_common(h, x, x_h, x_w, B, "leod_backbone_step_bwd"));
   LEOD_REQUIRE(save && h_out && c_out && dc_prev, "leod_backbone_step_bwd: null argument");
   LEOD_REQUIRE(h->grads, "leod_backbone_step_bwd: gradient buffer not bound");
+  h->col0_live = false;
   cudaStream_t st = (cudaStream_t)stream;
   LEOD_TRY(ensure_workspace(h, B, B));
   StageLayout lay[4], glay[4];
@@ -659,11 +681,24 @@ static int ensure_seq(leod_backbone *h, int B, int L) {
   LEOD_TRY(ensure_workspace(h, (int64_t)B * L, B));
   if (h->seq_arena && h->seq_B == B && h->seq_L == L) return 0;
   if (h->seq_arena) cudaFree(h->seq_arena);
-  h->seq_arena = nullptr;
+  if (h->seq_col0) cudaFree(h->seq_col0);
+  h->seq_arena = h->seq_col0 = nullptr;
+  h->seq_col0_imgs = 0;
   StageLayout lay[4];
   int64_t n;
   compute_layout(h, B, L, true, true, lay, &n);
   LEOD_CUDA(cudaMalloc(&h->seq_arena, n * (int64_t)h->esz()));
+  {
+    const StageD &d0 = h->d[0];
+    const int64_t rows = (int64_t)B * L * d0.Ho * d0.Wo;
+    if (rows * d0.Kp < (1LL << 31) * 4 && rows < (1LL << 31) &&
+        cudaMalloc(&h->seq_col0, rows * d0.Kp * (int64_t)h->esz()) == cudaSuccess) {
+      h->seq_col0_imgs = (int64_t)B * L;
+    } else {
+      cudaGetLastError();   // not enough memory: fall back to chunked re-gathering
+      h->seq_col0 = nullptr;
+    }
+  }
   h->seq_B = B;
   h->seq_L = L;
   return 0;
@@ -688,6 +723,7 @@ extern "C" int leod_backbone_seq_fwd(leod_backbone_t *h, const void *x, int x_dt
   int64_t n;
   compute_layout(h, B, L, true, true, lay, &n);
   const int64_t e = (int64_t)h->esz();
+  h->col0_live = true;
   // Stage-major ("layer-wise") schedule.  Stage s at time t needs stage s-1 at time t and its own state at t-1; there
   // is no top-down feedback, so a whole stage can run over all L timesteps before the next one starts.  Everything but
   // the hidden-state half of the ConvLSTM gates is then batched over the L*B frames of the window; only
@@ -774,6 +810,7 @@ extern "C" int leod_backbone_seq_bwd(leod_backbone_t *h, const void *x, int x_dt
       LEOD_TRY(gemm_tn(h, (char *)g.dgates + M * 4 * C * e, 4 * C, h_all[s], C, dWl_h, 2 * C, nullptr, (int)((L - 1) * M), 4 * C, C, st));
     if (h0 && h0[s]) LEOD_TRY(gemm_tn(h, g.dgates, 4 * C, h0[s], C, dWl_h, 2 * C, nullptr, (int)M, 4 * C, C, st));
   }
+  h->col0_live = false;
   return 0;
 }
 
@@ -787,9 +824,12 @@ extern "C" int leod_backbone_grads_finalize(leod_backbone_t *h, void *stream) {
     const StageP &p = h->p[s];
     const StageW &w = h->w[s];
     const int C = d.C, R = h->cfg.mlp_ratio;
-    if (s > 0) {
+    {
       const int64_t n = (int64_t)C * d.K;
-      conv_grad_unpermute_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w.Gconv, G + p.convw, C, d.Cin, d.ksz);
+      if (s > 0)
+        conv_grad_unpermute_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w.Gconv, G + p.convw, C, d.Cin, d.ksz);
+      else
+        stem_grad_unpermute_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w.Gconv, G + p.convw, C, d.Cin, d.ksz);
       LEOD_LAUNCH_CHECK();
     }
     for (int b = 0; b < 2; ++b) {

@@ -118,6 +118,192 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const T *__restrict__ x, co
   }
 }
 
+// ------------------------------------------------------------------ LayerNorm, bf16 fast path (C % 8 == 0)
+// LPR lanes share a token; every lane owns NCH chunks of 8 channels (one 16-byte load each), so a warp reads
+// 32/LPR whole rows with full-width accesses instead of 2-byte strided ones.
+__device__ __forceinline__ void bf16x8_to_f(const uint4 &u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 f_to_bf16x8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    w[j] = *reinterpret_cast<const uint32_t *>(&p);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int LPR, int NCH>
+__global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(const bf16 *__restrict__ x, const float *__restrict__ w,
+                                                          const float *__restrict__ b, bf16 *__restrict__ y, int M, int C, float eps) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const int nchunk = C >> 3;
+  const bool row_ok = row < M;
+  float v[NCH][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int ch = sub + LPR * i;
+    if (row_ok && ch < nchunk) {
+      bf16x8_to_f(*reinterpret_cast<const uint4 *>(x + (size_t)row * C + ch * 8), v[i]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[i][j];
+  }
+  const float mean = group_sum<LPR>(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    if (sub + LPR * i < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(group_sum<LPR>(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int ch = sub + LPR * i;
+    if (row_ok && ch < nchunk) {
+      float wv[8], bv[8], o[8];
+      *reinterpret_cast<float4 *>(wv) = __ldg(reinterpret_cast<const float4 *>(w + ch * 8));
+      *reinterpret_cast<float4 *>(wv + 4) = __ldg(reinterpret_cast<const float4 *>(w + ch * 8 + 4));
+      *reinterpret_cast<float4 *>(bv) = __ldg(reinterpret_cast<const float4 *>(b + ch * 8));
+      *reinterpret_cast<float4 *>(bv + 4) = __ldg(reinterpret_cast<const float4 *>(b + ch * 8 + 4));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * wv[j] + bv[j];
+      *reinterpret_cast<uint4 *>(y + (size_t)row * C + ch * 8) = f_to_bf16x8(o);
+    }
+  }
+}
+
+template <int LPR, int NCH>
+__global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const bf16 *__restrict__ x, const float *__restrict__ w,
+                                                          const bf16 *__restrict__ dy, const bf16 *__restrict__ dres,
+                                                          bf16 *__restrict__ dx, float *__restrict__ dw, float *__restrict__ db, int M,
+                                                          int C, float eps) {
+  constexpr int RPW = 32 / LPR;
+  __shared__ float sdw[LN_MAX_C], sdb[LN_MAX_C];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sdw[i] = sdb[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane % LPR;
+  const int nchunk = C >> 3;
+  const int warps_total = gridDim.x * (blockDim.x >> 5);
+  float wv[NCH][8], dwacc[NCH][8], dbacc[NCH][8];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int ch = sub + LPR * i;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wv[i][j] = ch < nchunk ? w[ch * 8 + j] : 0.f;
+      dwacc[i][j] = dbacc[i][j] = 0.f;
+    }
+  }
+  for (int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;; row += warps_total * RPW) {
+    // all lanes of a warp leave together: the first row of the warp decides
+    if (row - lane / LPR >= M) break;
+    const bool row_ok = row < M;
+    float v[NCH][8], g[NCH][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = sub + LPR * i;
+      if (row_ok && ch < nchunk) {
+        bf16x8_to_f(*reinterpret_cast<const uint4 *>(x + (size_t)row * C + ch * 8), v[i]);
+        bf16x8_to_f(*reinterpret_cast<const uint4 *>(dy + (size_t)row * C + ch * 8), g[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = g[i][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+    const float mean = group_sum<LPR>(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      if (sub + LPR * i < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          q += d * d;
+        }
+      }
+    }
+    const float rstd = rsqrtf(group_sum<LPR>(q) / C + eps);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      if (row_ok && sub + LPR * i < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (v[i][j] - mean) * rstd;
+          dwacc[i][j] += g[i][j] * xh;
+          dbacc[i][j] += g[i][j];
+          const float gw = g[i][j] * wv[i][j];
+          v[i][j] = xh;
+          g[i][j] = gw;
+          c1 += gw;
+          c2 += gw * xh;
+        }
+      }
+    }
+    c1 = group_sum<LPR>(c1) / C;
+    c2 = group_sum<LPR>(c2) / C;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int ch = sub + LPR * i;
+      if (row_ok && ch < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - c1 - v[i][j] * c2);
+        if (dres) {
+          float r[8];
+          bf16x8_to_f(*reinterpret_cast<const uint4 *>(dres + (size_t)row * C + ch * 8), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        *reinterpret_cast<uint4 *>(dx + (size_t)row * C + ch * 8) = f_to_bf16x8(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int ch = sub + LPR * i;
+    if (ch < nchunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sdw[ch * 8 + j], dwacc[i][j]);
+        atomicAdd(&sdb[ch * 8 + j], dbacc[i][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&dw[i], sdw[i]);
+    atomicAdd(&db[i], sdb[i]);
+  }
+}
+
 // ------------------------------------------------------------------ ConvLSTM gate math (rnn.py:57-68)
 template <typename T>
 __global__ void lstm_fwd_kernel(T *__restrict__ gates, const T *__restrict__ c_prev, T *__restrict__ h_out,
@@ -172,36 +358,44 @@ __global__ void add_kernel(const T *__restrict__ a, const T *__restrict__ b, T *
 
 // ------------------------------------------------------------------ patch gather for the strided convs
 // stem: x [B,Cin,xh,xw] channel-first (u8 / f32 / bf16), implicit zero pad to (Hp,Wp) and conv padding.
-// One thread produces 8 consecutive patch entries (one 16-byte store for bf16); the k -> (cin,ky,kx)
-// decomposition comes from a shared-memory table instead of per-element divisions.
+// Patch layout: k = (cin*ksz + ky)*8 + slot, slot 0 <-> kx = -1 (its weight is zero), slots 1..7 <-> kx = 0..6, so one
+// 16-byte chunk of a patch row is 8 consecutive input pixels starting at a 4-aligned column (stride 4, pad 3):
+// two 32-bit loads for uint8 input instead of eight byte gathers.  One thread = one chunk.
 template <typename TI, typename T>
 __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI *__restrict__ x, T *__restrict__ col, int B, int Cin, int xh,
-                                                          int xw, int Ho, int Wo, int ksz, int stride, int pad, int K, int ldcol) {
-  extern __shared__ int ktab[];  // per k: (cin*xh*xw + ky*xw + kx) << 8 | ky << 4 | kx
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const int kx = k % ksz, ky = (k / ksz) % ksz, cin = k / (ksz * ksz);
-    ktab[k] = ((cin * xh * xw + ky * xw + kx) << 8) | (ky << 4) | kx;
-  }
-  __syncthreads();
-  const int chunks = ldcol / 8;
+                                                          int xw, int Ho, int Wo, int ksz, int stride, int pad, int ldcol) {
+  const int chunks = Cin * ksz;   // == ldcol / 8
   const int64_t total = (int64_t)B * Ho * Wo * chunks;
+  const bool word_path = sizeof(TI) == 1 && (xw & 3) == 0 && ((stride * 1 - pad - 1) & 3) == 0 && (stride & 3) == 0 &&
+                         ((uintptr_t)x & 3) == 0;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int ch = (int)(idx % chunks);
     const int64_t m = idx / chunks;
     const int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho), b = (int)(m / ((int64_t)Wo * Ho));
-    const int iy0 = oy * stride - pad, ix0 = ox * stride - pad;
-    const TI *base = x + (size_t)b * Cin * xh * xw + (int64_t)iy0 * xw + ix0;
+    const int cin = ch / ksz, ky = ch - cin * ksz;
+    const int iy = oy * stride - pad + ky, ix0 = ox * stride - pad - 1;
     __align__(16) T vals[8];
+    if (iy < 0 || iy >= xh) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = ch * 8 + j;
-      float v = 0.f;
-      if (k < K) {
-        const int e = ktab[k];
-        const int iy = iy0 + ((e >> 4) & 15), ix = ix0 + (e & 15);
-        if (iy >= 0 && iy < xh && ix >= 0 && ix < xw) v = to_f<TI>(base[e >> 8]);
+      for (int j = 0; j < 8; ++j) vals[j] = from_f<T>(0.f);
+    } else {
+      const TI *row = x + ((size_t)b * Cin + cin) * xh * xw + (size_t)iy * xw;
+      if (word_path) {
+        uint32_t w0 = 0, w1 = 0;
+        if (ix0 >= 0 && ix0 + 3 < xw) w0 = *reinterpret_cast<const uint32_t *>(row + ix0);
+        if (ix0 + 4 >= 0 && ix0 + 7 < xw) w1 = *reinterpret_cast<const uint32_t *>(row + ix0 + 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          vals[j] = from_f<T>((float)((w0 >> (8 * j)) & 0xffu));
+          vals[4 + j] = from_f<T>((float)((w1 >> (8 * j)) & 0xffu));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ix = ix0 + j;
+          vals[j] = from_f<T>((j > 0 && j <= ksz && ix >= 0 && ix < xw) ? to_f<TI>(row[ix]) : 0.f);
+        }
       }
-      vals[j] = from_f<T>(v);
     }
     T *dst = col + (size_t)m * ldcol + ch * 8;
     if (sizeof(T) == 2) {
@@ -292,11 +486,16 @@ __global__ void prep_weight_kernel(const float *__restrict__ src, const float *_
   if (idx >= (int64_t)N * K) return;
   const int n = (int)(idx / K), k = (int)(idx % K);
   size_t si = idx;
+  bool zero = false;
   if (perm == 1) {
     const int cin = k % Cin, kx = (k / Cin) % ksz, ky = k / (Cin * ksz);
     si = (((size_t)n * Cin + cin) * ksz + ky) * ksz + kx;
+  } else if (perm == 2) {   // stem: k = (cin*ksz + ky)*8 + slot, slot 0 unused, slots 1..ksz <-> kx
+    const int slot = k & 7, r = k >> 3;
+    zero = slot == 0 || slot > ksz;
+    si = (size_t)n * Cin * ksz * ksz + (size_t)r * ksz + (slot - 1);
   }
-  float v = src[si];
+  float v = zero ? 0.f : src[si];
   if (scale) v *= scale[n];
   const T t = from_f<T>(v);
   if (dst) dst[(size_t)n * ldd + k] = t;
@@ -348,6 +547,16 @@ inline int blocks_for(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
 int layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void *y, int M, int C, float eps, cudaStream_t st) {
   ProfScope ps(PK_LAYERNORM, 8.0 * M * C, 2.0 * M * C * dtype_size(dtype), st, M, C, 0);
   LEOD_REQUIRE(C <= LN_MAX_C, "layernorm: C=%d > %d", C, LN_MAX_C);
+  if (dtype == LEOD_BF16 && C % 8 == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)w) | ((uintptr_t)b)) & 15) == 0) {
+    const int nchunk = C / 8;
+#define LN_FWD_FAST(LPR, NCH)                                                                                         \
+  ln_fwd_bf16_kernel<LPR, NCH><<<ceil_div(M, 8 * (32 / LPR)), 256, 0, st>>>((const bf16 *)x, w, b, (bf16 *)y, M, C, eps)
+    if (nchunk <= 8) { LN_FWD_FAST(8, 1); } else if (nchunk <= 16) { LN_FWD_FAST(16, 1); } else if (nchunk <= 32) { LN_FWD_FAST(32, 1); }
+    else { LN_FWD_FAST(32, 2); }
+#undef LN_FWD_FAST
+    LEOD_LAUNCH_CHECK();
+    return 0;
+  }
 #define LN_FWD(NV) DISPATCH_T(dtype, (ln_fwd_kernel<T, NV><<<ceil_div(M, 8), 256, 0, st>>>((const T *)x, w, b, (T *)y, M, C, eps)))
   const int nv = ceil_div(C, 32);
   if (nv <= 1) { LN_FWD(1); } else if (nv <= 2) { LN_FWD(2); } else if (nv <= 3) { LN_FWD(3); } else if (nv <= 4) { LN_FWD(4); }
@@ -361,6 +570,18 @@ int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, cons
                   int M, int C, float eps, cudaStream_t st) {
   ProfScope ps(PK_LAYERNORM, 16.0 * M * C, (dres ? 4.0 : 3.0) * M * C * dtype_size(dtype), st, M, C, 1);
   LEOD_REQUIRE(C <= LN_MAX_C, "layernorm: C=%d > %d", C, LN_MAX_C);
+  if (dtype == LEOD_BF16 && C % 8 == 0 &&
+      ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dres) | ((uintptr_t)dx)) & 15) == 0) {
+    const int nchunk = C / 8;
+#define LN_BWD_FAST(LPR, NCH)                                                                                          \
+  ln_bwd_bf16_kernel<LPR, NCH><<<std::max(1, std::min(ceil_div(M, 8 * (32 / LPR)), 148 * 4)), 256, 0, st>>>(             \
+      (const bf16 *)x, w, (const bf16 *)dy, (const bf16 *)dres, (bf16 *)dx, dw, db, M, C, eps)
+    if (nchunk <= 8) { LN_BWD_FAST(8, 1); } else if (nchunk <= 16) { LN_BWD_FAST(16, 1); } else if (nchunk <= 32) { LN_BWD_FAST(32, 1); }
+    else { LN_BWD_FAST(32, 2); }
+#undef LN_BWD_FAST
+    LEOD_LAUNCH_CHECK();
+    return 0;
+  }
   int blocks = ceil_div(M, 8);          // one row per warp until the grid covers the GPU a few times over
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
@@ -405,16 +626,13 @@ int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin
                 int stride, int pad, int ldcol, cudaStream_t st) {
   ProfScope ps(PK_PATCH, 0.0, (double)B * (Hp / stride) * (Wp / stride) * ldcol * dtype_size(dtype) + (double)B * Cin * xh * xw * dtype_size(x_dtype), st, B, Cin, 0);
   const int Ho = (Hp + 2 * pad - ksz) / stride + 1, Wo = (Wp + 2 * pad - ksz) / stride + 1;
-  const int K = Cin * ksz * ksz;
-  LEOD_REQUIRE(ldcol % 8 == 0 && ksz <= 15 && K * sizeof(int) <= 40 * 1024 && (int64_t)Cin * xh * xw < (1 << 23),
-               "im2col_nchw: unsupported geometry (Cin*H*W must be < 2^23)");
+  LEOD_REQUIRE(ksz <= 7 && ldcol == Cin * ksz * 8, "im2col_nchw: patch pitch %d != Cin*ksz*8 (ksz=%d)", ldcol, ksz);
   const int64_t n = (int64_t)B * Ho * Wo * (ldcol / 8);
   int nb = blocks_for(n, 256);
-  if (nb > 148 * 16) nb = 148 * 16;
-  const size_t tab = (size_t)K * sizeof(int);
+  if (nb > 148 * 32) nb = 148 * 32;
 #define IM2COL_CASE(TI)                                                                                                     \
-  DISPATCH_T(dtype, (im2col_nchw_kernel<TI, T><<<nb, 256, tab, st>>>((const TI *)x, (T *)col, B, Cin, xh, xw, Ho, Wo, ksz, stride, \
-                                                                   pad, K, ldcol)))
+  DISPATCH_T(dtype, (im2col_nchw_kernel<TI, T><<<nb, 256, 0, st>>>((const TI *)x, (T *)col, B, Cin, xh, xw, Ho, Wo, ksz, stride, \
+                                                                 pad, ldcol)))
   if (x_dtype == LEOD_U8) {
     IM2COL_CASE(uint8_t);
   } else if (x_dtype == LEOD_BF16) {

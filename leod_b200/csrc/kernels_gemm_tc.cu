@@ -657,6 +657,13 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
           v.z += __uint_as_float(r[4 * q + 2]); v.w += __uint_as_float(r[4 * q + 3]);
           reinterpret_cast<float4 *>(dst)[q] = v;
         }
+      } else if (k0 + c + 16 <= a.K && (((uintptr_t)dst) & 15) == 0) {
+        // split-M partial sums: vector reductions (4 floats per L2 operation)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "f"(__uint_as_float(r[4 * q])),
+                       "f"(__uint_as_float(r[4 * q + 1])), "f"(__uint_as_float(r[4 * q + 2])), "f"(__uint_as_float(r[4 * q + 3]))
+                       : "memory");
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j)

@@ -73,12 +73,30 @@ class YOLOXHead(nn.Module):
 
     def forward(self, xin, labels=None, pred_probs=None):
         assert pred_probs is None
-        raw = []
-        for k, x in enumerate(xin):
+        def level(k, x):
             x = self.stems[k](x)
             cls_feat = self.cls_convs[k](x)
             reg_feat = self.reg_convs[k](x)
-            raw.append(torch.cat((self.reg_preds[k](reg_feat), self.obj_preds[k](reg_feat), self.cls_preds[k](cls_feat)), 1))
+            return torch.cat((self.reg_preds[k](reg_feat), self.obj_preds[k](reg_feat), self.cls_preds[k](cls_feat)), 1)
+
+        if xin[0].is_cuda and torch.cuda.is_current_stream_capturing():
+            # CUDA-graph capture (detector.py, _GraphedDetect): the three pyramid levels are independent chains of small
+            # kernels; fork them onto side streams so the captured graph (forward and backward) runs them side by side
+            cur = torch.cuda.current_stream()
+            if not hasattr(self, '_side_streams'):
+                self._side_streams = [torch.cuda.Stream() for _ in range(len(xin) - 1)]
+            raw = [None] * len(xin)
+            for k in range(1, len(xin)):
+                st = self._side_streams[k - 1]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    raw[k] = level(k, xin[k])
+                    raw[k].record_stream(cur)
+            raw[0] = level(0, xin[0])
+            for st in self._side_streams:
+                cur.wait_stream(st)
+        else:
+            raw = [level(k, x) for k, x in enumerate(xin)]
         hws = [tuple(r.shape[-2:]) for r in raw]
         self.hw = hws
         flat = torch.cat([r.flatten(2) for r in raw], 2).permute(0, 2, 1).float()  # [B, A, 5+C], level-major anchors
