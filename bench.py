@@ -10,6 +10,7 @@ YOLOX neck/head + SimOTA loss on the labelled frames, gradient clip + AdamW.  me
 Prints ONE JSON line on rank 0.
 """
 import argparse
+import datetime
 import json
 import os
 import subprocess
@@ -151,6 +152,93 @@ def run_reference(args, rank, world):
         'gpu_launches': 0}))
 
 
+def run_sweep(args, rank, local_rank, world):
+    """Secondary workload (BASELINE configs[3] shape): the teacher pseudo-label sweep — PseudoLabeler.predict_step on
+    chunks of 16 Gen1 sequences x 21 frames with hflip TTA (32 views), head + NMS + label filters on every frame.
+    Sequences are sharded over ranks (no data-path collective); metric = view-frames/s through backbone+head+NMS."""
+    import torch
+    import torch.distributed as dist
+    from leod_b200 import _lib
+    from leod_b200.config import Node, make_model_cfg
+    from leod_b200.data.labels import SparselyBatchedObjectLabels
+    from leod_b200.data.utils.types import DataType
+    from leod_b200.modules.pseudo_labeler import PseudoLabeler
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
+    torch.manual_seed(0)
+    SB = 16
+    mcfg = make_model_cfg(size='small', dataset='gen1', compute_dtype=args.dtype, conf_thre=0.01)
+    full = Node(model=mcfg, dataset=dict(sequence_length=L, name='gen1', downsample_by_factor_2=False),
+                tta=dict(enable=True, hflip=True, tflip=False), use_gt=True)
+    pl = PseudoLabeler(full).to(dev).eval()
+    g = torch.Generator().manual_seed(100 + rank)
+    host = []
+    for i in range(3):
+        ev = (torch.rand(L, SB, CIN, FH, FW, generator=g) < 0.1)
+        ev = (ev * (1 + torch.poisson(torch.full((L, SB, CIN, FH, FW), 1.5), generator=g)).clamp(max=255)).to(torch.uint8).pin_memory()
+        host.append(ev)
+    none_labels = [SparselyBatchedObjectLabels([None] * SB) for _ in range(L)]
+
+    def batch_of(ev_dev, first):
+        return {'worker_id': 0, 'data': {DataType.EV_REPR: ev_dev, DataType.OBJLABELS_SEQ: none_labels,
+                                         DataType.SKIPPED_OBJLABELS_SEQ: none_labels,
+                                         DataType.IS_FIRST_SAMPLE: torch.full((SB,), first, dtype=torch.bool)}}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    resident = [e.to(dev) for e in host]
+    lib = _lib.lib()
+    for i in range(args.warmup):
+        pl.predict_step(batch_of(resident[i % 3], i == 0))
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.leod_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = pl.predict_step(batch_of(resident[i % 3], False))
+    e1.record()
+    barrier()
+    launches = lib.leod_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    frames = world * 2 * SB * L * args.steps
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        out = pl.predict_step(batch_of(host[i % 3].to(dev, non_blocking=True), False))
+        n_boxes = sum(len(l) for row in out[0] for l in row if l is not None)    # labels read back on the host
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = frames / (float(t) * 1e-3)
+    if rank == 0:
+        print(json.dumps({
+            'metric': 'event-frames/s (teacher sweep: backbone + head + NMS + label filters) RVT-S Gen1 seq-len 21', 'value': frames / (ms * 1e-3),
+            'unit': 'event-frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': 'teacher pseudo-label sweep, RVT-small Gen1 240x304, 16 sequences x 21 frames per step per GPU, hflip TTA '
+                                   '(32 views), head+NMS on every frame, conf 0.01, nms 0.45, thresholds (0.6, 0.3) (BASELINE configs[3] shape)',
+                       'note': 'random-init weights: almost no box passes the confidence filter, NMS work is minimal',
+                       'parallelism': f'dp{world} (sequences sharded, no collective)'},
+            'e2e': {'value': e2e, 'unit': 'event-frames/s', 'h2d_bytes_per_step': host[0].numel(), 'd2h_bytes_per_step': 4 * 2 * SB * L},
+            'gpu_launches': int(launches), 'roofline': None, 'cpu_baseline': None, 'clocks': clocks, 'labels_last_step': n_boxes}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -162,6 +250,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-kinds', action='store_true', help='print the per-kernel-class breakdown to stderr')
     ap.add_argument('--profile-csv', default=None, help='write one line per launch of the roofline pass to this CSV')
+    ap.add_argument('--workload', default='train', choices=['train', 'sweep'],
+                    help='train: BASELINE configs[1] (the headline metric); sweep: teacher pseudo-label sweep, configs[3] shape')
     ap.add_argument('--no-graph-head', action='store_true', help='run neck/head/loss eagerly instead of replaying a CUDA graph')
     ap.add_argument('--phases', action='store_true', help='after the timed regions, time the phases of 3 extra steps (stderr)')
     args = ap.parse_args()
@@ -170,6 +260,8 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', 1))
     if args.impl == 'reference':
         return run_reference(args, rank, world)
+    if args.workload == 'sweep':
+        return run_sweep(args, rank, local_rank, world)
     assert args.warmup >= 3, 'timing rules: at least 3 warm-up steps'
 
     import torch
@@ -181,7 +273,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
     torch.manual_seed(0)
     full_cfg = Node(model=make_model_cfg(size='small', dataset='gen1', compute_dtype=args.dtype),
                     dataset=dict(sequence_length=L, name='gen1'))
@@ -197,13 +289,10 @@ def main():
         bb.set_gemm_impl(args.gemm_impl)
     opt = FlatOptimizer(module.mdl, lr=2e-4, weight_decay=0.0, clip_value=1.0)
     if world > 1:
-        for p, _ in opt.bufs:            # identical replicas, as DDP's initial broadcast
-            dist.broadcast(p, 0)
+        from leod_b200.modules.utils.distributed import allreduce_mean_, broadcast_flat
+        broadcast_flat([p for p, _ in opt.bufs], src=0)      # identical replicas, as DDP's initial broadcast
         bb.mark_params_updated()
-
-        def sync(flat_grad):
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
-        bb.grad_sync = sync
+        bb.grad_sync = lambda flat_grad: allreduce_mean_([flat_grad])
 
     # several distinct batches so consecutive steps do not re-read the same 25 MB of input
     n_batches = 4
@@ -215,7 +304,7 @@ def main():
         out = module.training_step(make_batch(ev_dev, labels, first))
         out['loss'].backward()
         if world > 1:
-            dist.all_reduce(opt.rest_grad, op=dist.ReduceOp.AVG)
+            allreduce_mean_([opt.rest_grad])
         opt.step()
         return out['loss']
 
@@ -273,8 +362,9 @@ def main():
         lib.leod_profile_enable(1)
         if args.profile_csv:
             lib.leod_profile_csv(args.profile_csv.encode())
-        train_step(*resident[0])
-        torch.cuda.synchronize()
+    train_step(*resident[0])          # every rank takes part (the step contains collectives); only rank 0 records
+    torch.cuda.synchronize()
+    if rank == 0:
         kinds = _lib.profile_collect()
         lib.leod_profile_enable(0)
         lib.leod_profile_csv(None)

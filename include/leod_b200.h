@@ -173,6 +173,15 @@ int leod_pred2label(const float *dets, const int32_t *count, int B, int max_det,
                     const float *obj_thresh, const float *cls_thresh, int frame_h, int frame_w, float *labels,
                     int32_t *lab_count, void *stream);
 
+/* Replaces modules/pseudo_labeler.py:37-91 (tta_postprocess, also modules/utils/tta.py:18-61): the second NMS over
+ * the concatenated test-time-augmentation views of a frame, batched over frames.
+ *  labels    : device fp32 [F, nmax, 8] ObjectLabels rows (t, x, y, w, h, cls, cls_conf, obj_conf), corner format
+ *  count     : device int32 [F] valid rows per frame
+ *  out/out_count : same layout; kept rows in descending obj*cls_conf order with w,h = (x+w)-x, (y+h)-y as the
+ *              reference's xyxy round trip produces them.  Frames holding ground truth (any t > 0) are copied through. */
+int leod_tta_merge(const float *labels, const int32_t *count, int F, int nmax, float conf_thre, float nms_thre,
+                   int class_agnostic, float *out, int32_t *out_count, void *stream);
+
 /* ------------------------------------------------------------------ event binning
  * Replaces data/utils/representations.py:78-123 (StackedHistogram.construct).
  * x,y,p: device int32 [n]; t: device int64 [n] (sorted); out: device uint8 [2*bins, H, W].

@@ -61,6 +61,7 @@ def _declare(lib):
         'leod_lstm_gates_bwd': (I, [I, VP, VP, VP, VP, VP, VP, VP, VP, I, I, VP]),
         'leod_postprocess': (I, [VP, I, I, I, F, F, I, VP, VP, I, VP]),
         'leod_pred2label': (I, [VP, VP, I, I, I, POINTER(c_float), POINTER(c_float), I, I, VP, VP, VP]),
+        'leod_tta_merge': (I, [VP, VP, I, I, F, F, I, VP, VP, VP]),
         'leod_voxel_bin': (I, [VP, VP, VP, VP, c_int64, I, I, I, I, I, VP, VP]),
         'leod_adamw_ema': (I, [VP, VP, VP, VP, VP, c_int64, I, F, F, F, F, F, F, F, VP]),
     }
@@ -79,7 +80,7 @@ EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 
                     'leod_backbone_step_fwd', 'leod_backbone_step_bwd', 'leod_backbone_grads_finalize', 'leod_backbone_seq_arena_bytes',
                     'leod_backbone_seq_fwd', 'leod_backbone_seq_bwd', 'leod_gemm_nt',
                     'leod_gemm_tn', 'leod_attention_fwd', 'leod_attention_bwd', 'leod_layernorm_fwd', 'leod_layernorm_bwd',
-                    'leod_lstm_gates_fwd', 'leod_lstm_gates_bwd', 'leod_postprocess', 'leod_pred2label',
+                    'leod_lstm_gates_fwd', 'leod_lstm_gates_bwd', 'leod_postprocess', 'leod_pred2label', 'leod_tta_merge',
                     'leod_voxel_bin', 'leod_adamw_ema']
 
 

@@ -30,9 +30,15 @@ DATASETS = {'gen1': dict(partition_size=(8, 10), num_classes=2, in_res_hw=(256, 
             'gen4': dict(partition_size=(6, 10), num_classes=3, in_res_hw=(384, 640), frame_hw=(360, 640))}
 
 
+def _default_thresh(num_classes):
+    """gen1 (car, ped) -> [0.6, 0.3]; gen4 (ped, cyc, car) -> [0.3, 0.3, 0.6] would need the dataset's class order:
+    the reference re-orders at run time (config/modifier.py:88-108); here extra classes just take 0.3."""
+    return ([0.6, 0.3] + [0.3] * max(0, num_classes - 2))[:num_classes]
+
+
 def make_model_cfg(size=None, dataset=None, embed_dim=None, dim_head=None, partition_size=None, num_classes=None,
                    fpn_depth=None, input_channels=20, in_res_hw=None, ignore_bbox_thresh=None, compute_dtype='bf16',
-                   conf_thre=0.1, nms_thre=0.45):
+                   conf_thre=0.1, nms_thre=0.45, pseudo_label=None):
     if size is not None:
         e, dh, dep = SIZES[size]
         embed_dim = embed_dim or e
@@ -61,4 +67,7 @@ def make_model_cfg(size=None, dataset=None, embed_dim=None, dim_head=None, parti
         head=dict(name='YoloX', compile=dict(enable=False, args={}), depthwise=False, act='silu', num_classes=num_classes,
                   obj_focal_loss=False, bbox_loss_weighting='', ignore_bbox_thresh=ignore_bbox_thresh, ignore_label=1024,
                   ignore_bg_k=0),
-        postprocess=dict(confidence_threshold=conf_thre, nms_threshold=nms_thre))
+        postprocess=dict(confidence_threshold=conf_thre, nms_threshold=nms_thre),
+        # config/model/pseudo_labeler.yaml:15-21 (read by modules/pseudo_labeler.py only)
+        pseudo_label=dict(pseudo_label or dict(skip_first_t=0, obj_thresh=_default_thresh(num_classes),
+                                               cls_thresh=_default_thresh(num_classes))))

@@ -282,7 +282,8 @@ int front_fwd(leod_backbone *h, int s, int64_t nimg, const void *in, int x_dtype
   const float *P = h->params;
   const int64_t rows_per_img = (int64_t)d.Ho * d.Wo, e = (int64_t)h->esz();
   const int64_t M64 = nimg * rows_per_img;
-  LEOD_REQUIRE(M64 * std::max(4 * C, d.Kp) < (1LL << 31), "stage %d: %lld rows exceed the 32-bit indexing of the kernels", s, (long long)M64);
+  // row indices are 32-bit in the kernels (element offsets are computed in 64 bits)
+  LEOD_REQUIRE(M64 < (1LL << 31) - 1024, "stage %d: %lld rows exceed the 32-bit row indexing of the kernels", s, (long long)M64);
   const int M = (int)M64;
   // the stem's patch matrix of a whole BPTT window is kept for the weight-gradient GEMM (seq_col0, sequence mode)
   const bool keep = s == 0 && h->col0_live && h->seq_col0 && nimg == h->seq_col0_imgs;

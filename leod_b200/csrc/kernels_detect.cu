@@ -157,6 +157,109 @@ __global__ void pred2label_kernel(const float *__restrict__ dets, const int32_t 
   if (lane == 0) lab_count[b] = base;
 }
 
+
+// Second NMS over the concatenated TTA views of one frame (modules/pseudo_labeler.py:37-91): rows are ObjectLabels
+// records (t, x, y, w, h, cls, cls_conf, obj); one CTA per frame.  Same order of float operations as the reference:
+// x2 = x + w, score = obj * cls_conf, offsets cls * (max coordinate of the kept candidates + 1), IoU > thr drops.
+constexpr int TM_THREADS = 128;
+__global__ void __launch_bounds__(TM_THREADS) tta_merge_kernel(const float *__restrict__ labels, const int32_t *__restrict__ count,
+                                                               int nmax, float conf_thre, float nms_thre, int class_agnostic,
+                                                               float *__restrict__ out, int32_t *__restrict__ out_count) {
+  extern __shared__ float sm[];
+  float *c_score = sm;                      // [nmax]
+  int *c_row = (int *)(c_score + nmax);     // [nmax]
+  int *s_row = c_row + nmax;                // [nmax]
+  float *s_box = (float *)(s_row + nmax);   // [4 nmax]
+  unsigned char *s_sup = (unsigned char *)(s_box + 4 * (size_t)nmax);
+  __shared__ int n_cand, n_keep;
+  __shared__ float red[TM_THREADS / 32];
+  __shared__ float max_coord_s;
+  const int f = blockIdx.x, tid = threadIdx.x;
+  const int n_in = min(count[f], nmax);
+  const float *L = labels + (size_t)f * nmax * 8;
+  float *O = out + (size_t)f * nmax * 8;
+  // frames that carry ground truth (t > 0 anywhere) pass through untouched (pseudo_labeler.py:50-53)
+  __shared__ int has_gt;
+  if (tid == 0) { n_cand = 0; n_keep = 0; has_gt = 0; }
+  __syncthreads();
+  for (int r = tid; r < n_in; r += TM_THREADS)
+    if (L[r * 8] > 0.f) has_gt = 1;
+  __syncthreads();
+  if (has_gt) {
+    for (int i = tid; i < n_in * 8; i += TM_THREADS) O[i] = L[i];
+    if (tid == 0) out_count[f] = n_in;
+    return;
+  }
+  float local_max = -INFINITY;
+  for (int r = tid; r < n_in; r += TM_THREADS) {
+    const float *q = L + r * 8;
+    const float score = __fmul_rn(q[7], q[6]);
+    if (score >= conf_thre) {
+      const int slot = atomicAdd(&n_cand, 1);
+      c_score[slot] = score;
+      c_row[slot] = r;
+      const float x2 = __fadd_rn(q[1], q[3]), y2 = __fadd_rn(q[2], q[4]);
+      local_max = fmaxf(local_max, fmaxf(fmaxf(q[1], q[2]), fmaxf(x2, y2)));
+    }
+  }
+  local_max = warp_max(local_max);
+  if ((tid & 31) == 0) red[tid >> 5] = local_max;
+  __syncthreads();
+  if (tid == 0) {
+    float m = red[0];
+    for (int i = 1; i < TM_THREADS / 32; ++i) m = fmaxf(m, red[i]);
+    max_coord_s = m;
+  }
+  __syncthreads();
+  const int n = n_cand;
+  const float off_unit = class_agnostic ? 0.f : __fadd_rn(max_coord_s, 1.0f);
+  for (int i = tid; i < n; i += TM_THREADS) {
+    const float si = c_score[i];
+    const int ri = c_row[i];
+    int rank = 0;
+    for (int j = 0; j < n; ++j) {
+      const float sj = c_score[j];
+      rank += (sj > si) || (sj == si && c_row[j] < ri);
+    }
+    const float *q = L + ri * 8;
+    const float off = __fmul_rn(q[5], off_unit);
+    s_row[rank] = ri;
+    s_box[4 * rank + 0] = __fadd_rn(q[1], off);
+    s_box[4 * rank + 1] = __fadd_rn(q[2], off);
+    s_box[4 * rank + 2] = __fadd_rn(__fadd_rn(q[1], q[3]), off);
+    s_box[4 * rank + 3] = __fadd_rn(__fadd_rn(q[2], q[4]), off);
+    s_sup[rank] = 0;
+  }
+  __syncthreads();
+  for (int i = 0; i < n; ++i) {
+    if (s_sup[i]) continue;
+    const int kslot = n_keep;
+    const float ix1 = s_box[4 * i], iy1 = s_box[4 * i + 1], ix2 = s_box[4 * i + 2], iy2 = s_box[4 * i + 3];
+    const float iarea = __fmul_rn(__fsub_rn(ix2, ix1), __fsub_rn(iy2, iy1));
+    for (int j = i + 1 + tid; j < n; j += TM_THREADS) {
+      if (s_sup[j]) continue;
+      const float jx1 = s_box[4 * j], jy1 = s_box[4 * j + 1], jx2 = s_box[4 * j + 2], jy2 = s_box[4 * j + 3];
+      const float w = fmaxf(__fsub_rn(fminf(ix2, jx2), fmaxf(ix1, jx1)), 0.f);
+      const float h = fmaxf(__fsub_rn(fminf(iy2, jy2), fmaxf(iy1, jy1)), 0.f);
+      const float inter = __fmul_rn(w, h);
+      const float jarea = __fmul_rn(__fsub_rn(jx2, jx1), __fsub_rn(jy2, jy1));
+      const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
+      if (iou > nms_thre) s_sup[j] = 1;
+    }
+    if (tid == 0) {
+      const float *q = L + s_row[i] * 8;
+      float *d = O + (size_t)kslot * 8;
+      const float x2 = __fadd_rn(q[1], q[3]), y2 = __fadd_rn(q[2], q[4]);
+      d[0] = q[0]; d[1] = q[1]; d[2] = q[2]; d[3] = __fsub_rn(x2, q[1]); d[4] = __fsub_rn(y2, q[2]);
+      d[5] = q[5]; d[6] = q[6]; d[7] = q[7];
+      n_keep = kslot + 1;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) out_count[f] = n_keep;
+}
+
 }  // namespace
 
 extern "C" int leod_postprocess(const float *pred, int B, int A, int num_classes, float conf_thre, float nms_thre,
@@ -190,6 +293,24 @@ extern "C" int leod_pred2label(const float *dets, const int32_t *count, int B, i
     th.cls_thr[i] = i < num_classes ? cls_thresh[i] : 2.f;
   }
   pred2label_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(dets, count, max_det, num_classes, th, frame_h, frame_w, labels, lab_count);
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int leod_tta_merge(const float *labels, const int32_t *count, int F, int nmax, float conf_thre, float nms_thre,
+                              int class_agnostic, float *out, int32_t *out_count, void *stream) {
+  LEOD_REQUIRE(labels && count && out && out_count, "leod_tta_merge: null argument");
+  LEOD_REQUIRE(F >= 0 && nmax > 0, "leod_tta_merge: bad sizes F=%d nmax=%d", F, nmax);
+  if (F == 0) return 0;
+  const size_t smem = (size_t)nmax * (4 + 4 + 4 + 16 + 1) + 16;
+  LEOD_REQUIRE(smem <= 220 * 1024, "leod_tta_merge: %d boxes per frame exceed the shared-memory budget", nmax);
+  static size_t smem_set = 0;
+  if (smem > smem_set && smem > 48 * 1024) {
+    LEOD_CUDA(cudaFuncSetAttribute(tta_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  tta_merge_kernel<<<F, TM_THREADS, smem, (cudaStream_t)stream>>>(labels, count, nmax, conf_thre, nms_thre, class_agnostic, out,
+                                                                  out_count);
   LEOD_LAUNCH_CHECK();
   return 0;
 }

@@ -24,6 +24,16 @@ class ObjectLabels:
     def is_gt_label(self):
         return self.object_labels[:, 0] > 0
 
+    def clone(self):
+        return ObjectLabels(self.object_labels.clone(), self.input_size_hw)
+
+    def flip_lr_(self) -> None:
+        """labels.py:506-509: mirror the boxes horizontally, in place (x <- W - 1 - x - w)."""
+        if len(self) == 0:
+            return
+        l = self.object_labels
+        l[:, 1] = self.input_size_hw[1] - 1 - l[:, 1] - l[:, 3]
+
     def get_labels_as_tensors(self, format_: str = 'yolox') -> torch.Tensor:
         """labels.py:543-571.  'yolox': [N,7] = (cls, cx, cy, w, h, obj_conf, cls_conf)."""
         l = self.object_labels
@@ -55,6 +65,24 @@ class SparselyBatchedObjectLabels:
 
     def __getitem__(self, i):
         return self.sparse_object_labels_batch[i]
+
+    def __iter__(self):
+        return iter(self.sparse_object_labels_batch)
+
+    def __add__(self, other: 'SparselyBatchedObjectLabels'):
+        """labels.py:~640: concatenate along the batch (used by the hflip TTA batch doubling)."""
+        return SparselyBatchedObjectLabels(self.sparse_object_labels_batch + other.sparse_object_labels_batch)
+
+    def is_empty(self):
+        return all(l is None for l in self.sparse_object_labels_batch)
+
+    def flip_lr_(self) -> None:
+        for l in self.sparse_object_labels_batch:
+            if l is not None:
+                l.flip_lr_()
+
+    def clone(self):
+        return SparselyBatchedObjectLabels([None if l is None else l.clone() for l in self.sparse_object_labels_batch])
 
     def get_valid_labels_and_batch_indices(self, ignore: bool = False, ignore_label: int = 1024):
         """labels.py:~700-730: entries that carry at least one box (optionally skipping frames whose

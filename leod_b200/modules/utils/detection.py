@@ -81,3 +81,30 @@ class RNNStates:
     def reset(self, worker_id: int, indices_or_bool_tensor: Optional[Union[List[int], th.Tensor]] = None):
         if worker_id in self.states:
             self.states[worker_id] = self.recursive_reset(self.states[worker_id], indices_or_bool_tensor)
+
+
+class SeqLens:
+    """How many timesteps of each streamed sequence have been seen (modules/utils/detection.py:160-192)."""
+
+    def __init__(self):
+        self.lens = {}
+
+    def update_lens(self, worker_id: int, lens: th.Tensor) -> None:
+        if worker_id not in self.lens:
+            self.lens[worker_id] = lens
+        else:
+            self.lens[worker_id] += lens
+
+    def get_lens(self, worker_id: int) -> Optional[th.Tensor]:
+        return self.lens.get(worker_id, None)
+
+    def reset(self, worker_id: int, indices_or_bool_tensor: Optional[Union[List[int], th.Tensor]] = None):
+        if worker_id not in self.lens:
+            self.lens[worker_id] = th.zeros(len(indices_or_bool_tensor)).long()
+            return
+        if indices_or_bool_tensor is None:
+            self.lens[worker_id] = th.zeros_like(self.lens[worker_id])
+        else:
+            assert len(indices_or_bool_tensor) > 0
+            idx = indices_or_bool_tensor.cpu() if th.is_tensor(indices_or_bool_tensor) else indices_or_bool_tensor
+            self.lens[worker_id][idx] = 0

@@ -57,6 +57,18 @@ def pred2label(pred: List[Optional[torch.Tensor]], obj_thresh=0.9, cls_thresh=0.
     return [labels[b, :k] for b, k in enumerate(n.tolist())]
 
 
+def tta_merge_packed(labels: torch.Tensor, count: torch.Tensor, conf_thre: float, nms_thre: float, class_agnostic: bool = False):
+    """labels [F,nmax,8] fp32 ObjectLabels rows + count [F] int32 -> (merged [F,nmax,8], n [F]): the second NMS of
+    modules/pseudo_labeler.py:37-91 for F frames in one launch (leod_tta_merge)."""
+    F, nmax, _ = labels.shape
+    out = torch.zeros_like(labels)
+    n = torch.zeros(F, dtype=torch.int32, device=labels.device)
+    with torch.cuda.device(labels.device):
+        _lib.check(_lib.lib().leod_tta_merge(_lib.ptr(labels.contiguous()), _lib.ptr(count), F, nmax, float(conf_thre), float(nms_thre),
+                                             int(class_agnostic), _lib.ptr(out), _lib.ptr(n), _lib.stream_ptr(labels.device)), 'tta_merge')
+    return out, n
+
+
 def ema_alpha_at(global_step: int, alpha: float = 0.999) -> float:
     """ssod.py:435: the true average until the exponential average is more correct."""
     return min(1. - 1. / (global_step + 1.), alpha)

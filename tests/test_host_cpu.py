@@ -120,3 +120,45 @@ def test_layout_query_needs_no_gpu():
     bad = _lib.BackboneCfg(20, 48, 24, 8, 10, 4, 250, 320, _lib.LEOD_BF16, 1e-5)
     assert l.leod_backbone_layout_only(ctypes.byref(bad), ctypes.byref(h)) != 0
     assert b'multiple of 32' in l.leod_last_error()
+
+
+def test_pseudo_labeler_masks_and_hflip_batch_doubling(net):
+    """Host logic of modules/pseudo_labeler.py:458-495 and :514-547 (no device work): TTA batch doubling duplicates
+    the metadata and mirrors the labels; frames with GT, padded frames and the first `skip_first_t` frames of a fresh
+    sequence are not predicted."""
+    from leod_b200.config import Node
+    from leod_b200.data.labels import ObjectLabels, SparselyBatchedObjectLabels
+    from leod_b200.data.utils.types import DataType
+    from leod_b200.modules.pseudo_labeler import PseudoLabeler
+    z, cfg, sd, d = net
+    H, W = d['H'], d['W']
+    mcfg = product_cfg(cfg, (H, W))
+    mcfg.pseudo_label = Node(skip_first_t=2, obj_thresh=[0.6, 0.3], cls_thresh=[0.6, 0.3])
+    full = Node(model=mcfg, dataset=dict(sequence_length=4, name='gen1', downsample_by_factor_2=False),
+                tta=dict(enable=True, hflip=True, tflip=True), use_gt=True)
+    pl = PseudoLabeler(full)
+    L, B = 4, 2
+    box = torch.tensor([[1., 10, 8, 20, 16, 0, 1, 1]])
+    obj = [SparselyBatchedObjectLabels([ObjectLabels(box.clone(), (H, W)) if (t, b) == (3, 1) else None for b in range(B)]) for t in range(L)]
+    skipped = [SparselyBatchedObjectLabels([None] * B) for _ in range(L)]
+    padded = [torch.tensor([False, False]) for _ in range(L)]
+    padded[2] = torch.tensor([True, False])
+    data = {DataType.EV_REPR: torch.zeros(L, B, cfg.input_channels, H, W, dtype=torch.uint8), DataType.OBJLABELS_SEQ: obj,
+            DataType.SKIPPED_OBJLABELS_SEQ: skipped, DataType.IS_FIRST_SAMPLE: torch.tensor([True, False]),
+            DataType.IS_LAST_SAMPLE: torch.tensor([False, False]), DataType.IS_REVERSED: torch.tensor([False, False]),
+            DataType.EV_IDX: [torch.full((B,), t) for t in range(L)], DataType.IS_PADDED_MASK: padded, DataType.PATH: ['a', 'b']}
+    out = pl.get_data_from_batch({'worker_id': 0, 'data': data})
+    assert out['EV_REPR'].shape[1] == 2 * B and out['EV_REPR'].dtype == torch.uint8
+    assert out['PATH'] == ['a', 'b', 'a', 'b'] and out['IS_FIRST_SAMPLE'].tolist() == [True, False, True, False]
+    assert list(out['is_hflip']) == [False, False, True, True]
+    flipped = out['OBJLABELS_SEQ'][3][3]
+    assert float(flipped.object_labels[0, 1]) == W - 1 - 10 - 20 and float(out['OBJLABELS_SEQ'][3][1].object_labels[0, 1]) == 10
+    # sequence 0 (and its mirrored view) is fresh, sequence 1 has 5 frames of history
+    pl.mode_2_seq_lens.lens[0] = torch.tensor([0, 5, 0, 5])
+    pse, gt, skipped_gt = pl._get_pred_mask(worker_id=0, data=out)
+    exp = np.ones((L, 2 * B), bool)
+    exp[:2, 0] = exp[:2, 2] = False           # skip_first_t
+    exp[2, 0] = exp[2, 2] = False             # padded
+    exp[3, 1] = exp[3, 3] = False             # ground truth present
+    np.testing.assert_array_equal(pse, exp)
+    assert gt.sum() == 2 and gt[3, 1] and gt[3, 3] and skipped_gt.sum() == 0
