@@ -55,6 +55,12 @@ class YOLOXHead(nn.Module):
         for conv in list(self.cls_preds) + list(self.obj_preds):
             nn.init.constant_(conv.bias, prior)
 
+    def _has_sync_bn(self):
+        # SyncBatchNorm layers issue collectives: keep them in one stream so every rank captures the same order
+        if not hasattr(self, '_sync_bn'):
+            self._sync_bn = any(isinstance(m, nn.SyncBatchNorm) for m in self.modules())
+        return self._sync_bn
+
     # ------------------------------------------------------------------ grids / decode
     def _grids(self, hws, device, dtype):
         key = (tuple(hws), str(device), dtype)
@@ -79,7 +85,7 @@ class YOLOXHead(nn.Module):
             reg_feat = self.reg_convs[k](x)
             return torch.cat((self.reg_preds[k](reg_feat), self.obj_preds[k](reg_feat), self.cls_preds[k](cls_feat)), 1)
 
-        if xin[0].is_cuda and torch.cuda.is_current_stream_capturing():
+        if xin[0].is_cuda and torch.cuda.is_current_stream_capturing() and not self._has_sync_bn():
             # CUDA-graph capture (detector.py, _GraphedDetect): the three pyramid levels are independent chains of small
             # kernels; fork them onto side streams so the captured graph (forward and backward) runs them side by side
             cur = torch.cuda.current_stream()
