@@ -2,7 +2,9 @@
 // 16 query rows, QK^T and PV (and the five backward products) on mma.sync.m16n8k16 with fp32
 // accumulation, softmax in registers.  The per-(window, head) problems are 80x80x24 / 60x60x32 —
 // far below a tcgen05 128-row tile — so the warp-level MMA is the right granularity here; the
-// partition index map is applied while staging q/k/v, so no permute copies exist.
+// partition index map is applied while staging q/k/v, so no permute copies exist.  Operands are staged
+// row-major once; every transposed view (V for PV, K for dQ, dS^T / P^T / Q / dO for dK and dV) is a
+// transposing ldmatrix, results leave through a shared-memory tile as 16-byte row pieces.
 #include "common.cuh"
 
 namespace {
@@ -28,85 +30,51 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t *>(&v);
 }
-// A fragment of the 16x16 block at (row0, k0) of a row-major [m][k] bf16 matrix with pitch ld
-__device__ __forceinline__ void load_a(uint32_t (&a)[4], const bf16 *A, int ld, int row0, int k0, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  const bf16 *p = A + (size_t)(row0 + g) * ld + k0 + 2 * t;
-  a[0] = *reinterpret_cast<const uint32_t *>(p);
-  a[1] = *reinterpret_cast<const uint32_t *>(p + 8 * ld);
-  a[2] = *reinterpret_cast<const uint32_t *>(p + 8);
-  a[3] = *reinterpret_cast<const uint32_t *>(p + 8 * ld + 8);
+// ---- ldmatrix fragment loaders (m16n8k16, bf16).  All matrices live in shared memory row-major with a pitch that is a
+// multiple of 16 bytes and conflict-free for 8 consecutive rows (80 B and 176 B pitches below).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-// B fragment (k16 x n8) from a matrix stored [n][k] (k contiguous) with pitch ld
-__device__ __forceinline__ void load_b(uint32_t &b0, uint32_t &b1, const bf16 *Bm, int ld, int n0, int k0, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  const bf16 *p = Bm + (size_t)(n0 + g) * ld + k0 + 2 * t;
-  b0 = *reinterpret_cast<const uint32_t *>(p);
-  b1 = *reinterpret_cast<const uint32_t *>(p + 8);
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t &r0, uint32_t &r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t &r0, uint32_t &r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+// A fragment (16 rows x 16 k) of a matrix stored [row][k]
+__device__ __forceinline__ void frag_a(uint32_t (&a)[4], const bf16 *M, int ld, int row0, int k0, int lane) {
+  ldsm_x4(a, smem_addr(M + (size_t)(row0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ld + k0 + (lane >> 4) * 8));
+}
+// A fragment of the TRANSPOSE of a matrix stored [k][row]: A[row0+i][k0+j] = M[k0+j][row0+i]
+__device__ __forceinline__ void frag_a_t(uint32_t (&a)[4], const bf16 *M, int ld, int row0, int k0, int lane) {
+  const int i = lane >> 3;
+  ldsm_x4_t(a, smem_addr(M + (size_t)(k0 + (lane & 7) + (i >> 1) * 8) * ld + row0 + (i & 1) * 8));
+}
+// B fragment (16 k x 8 n) of a matrix stored [n][k] (k contiguous)
+__device__ __forceinline__ void frag_b(uint32_t &b0, uint32_t &b1, const bf16 *M, int ld, int n0, int k0, int lane) {
+  ldsm_x2(b0, b1, smem_addr(M + (size_t)(n0 + (lane & 7)) * ld + k0 + ((lane >> 3) & 1) * 8));
+}
+// B fragment of a matrix stored [k][n] (n contiguous)
+__device__ __forceinline__ void frag_b_t(uint32_t &b0, uint32_t &b1, const bf16 *M, int ld, int n0, int k0, int lane) {
+  ldsm_x2_t(b0, b1, smem_addr(M + (size_t)(k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * ld + n0));
 }
 
-// NT_S: 8-column tiles of the score matrix (even); NT_O: dh / 8; KS: ceil(dh / 16)
-template <int NT_S, int NT_O, int KS>
-__global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16))
-    attn_fwd_tc_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int H, int W, int C, int ph, int pw, int window,
-                       float scale) {
-  constexpr int TP = ((NT_S * 8 + 15) / 16) * 16;  // padded tokens
-  constexpr int DH = NT_O * 8, DHP = KS * 16;
-  constexpr int LDQ = DHP + 8, LDT = TP + 8;
-  constexpr int NTHREADS = 32 * (TP / 16);
-  __shared__ __align__(16) bf16 sQ[TP * LDQ];
-  __shared__ __align__(16) bf16 sK[TP * LDQ];
-  __shared__ __align__(16) bf16 sVt[DH * LDT];
-  __shared__ int rows[TP];
-  const int T = ph * pw;
-  const int g = blockIdx.x, head = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < TP * LDQ / 2; i += NTHREADS) {
-    reinterpret_cast<uint32_t *>(sQ)[i] = 0u;
-    reinterpret_cast<uint32_t *>(sK)[i] = 0u;
-  }
-  for (int i = tid; i < DH * LDT / 2; i += NTHREADS) reinterpret_cast<uint32_t *>(sVt)[i] = 0u;
-  for (int t = tid; t < TP; t += NTHREADS) rows[t] = t < T ? token_row(g, t, H, W, ph, pw, window) : 0;
-  __syncthreads();
-  constexpr int VPR = DH / 8;  // 16-byte vectors per q/k/v row
-  for (int idx = tid; idx < T * 3 * VPR; idx += NTHREADS) {
-    const int t = idx / (3 * VPR), rem = idx % (3 * VPR), which = rem / VPR, v8 = rem % VPR;
-    const uint4 val = *reinterpret_cast<const uint4 *>(qkv + (size_t)rows[t] * 3 * C + head * 3 * DH + which * DH + v8 * 8);
-    if (which == 0) {
-      *reinterpret_cast<uint4 *>(&sQ[t * LDQ + v8 * 8]) = val;
-    } else if (which == 1) {
-      *reinterpret_cast<uint4 *>(&sK[t * LDQ + v8 * 8]) = val;
-    } else {
-      const bf16 *e = reinterpret_cast<const bf16 *>(&val);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sVt[(v8 * 8 + j) * LDT + t] = e[j];
-    }
-  }
-  __syncthreads();
-  const int row0 = warp * 16;
-  float s[NT_S][4];
-#pragma unroll
-  for (int n = 0; n < NT_S; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    uint32_t a[4];
-    load_a(a, sQ, LDQ, row0, ks * 16, lane);
-#pragma unroll
-    for (int n = 0; n < NT_S; ++n) {
-      uint32_t b0, b1;
-      load_b(b0, b1, sK, LDQ, n * 8, ks * 16, lane);
-      mma16816(s[n], a, b0, b1);
-    }
-  }
-  // softmax over the row (rows g and g+8 of this warp's slab); columns >= T are padding
-  const int tq = lane & 3;
+template <int NT_S>
+__device__ __forceinline__ void softmax_rows(float (&s)[NT_S][4], int T, float scale, int tq, float &inv0, float &inv1) {
+  // rows g and g+8 of the warp's 16-row slab; columns >= T are padding.  exp via ex2 with log2(e) folded into the scale.
+  const float sl = scale * 1.4426950408889634f;
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
   for (int n = 0; n < NT_S; ++n) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const bool ok = n * 8 + 2 * tq + e < T;
-      s[n][e] = ok ? s[n][e] * scale : -INFINITY;
-      s[n][2 + e] = ok ? s[n][2 + e] * scale : -INFINITY;
+      s[n][e] = ok ? s[n][e] * sl : -INFINITY;
+      s[n][2 + e] = ok ? s[n][2 + e] * sl : -INFINITY;
       mx0 = fmaxf(mx0, s[n][e]);
       mx1 = fmaxf(mx1, s[n][2 + e]);
     }
@@ -120,8 +88,8 @@ __global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16))
   for (int n = 0; n < NT_S; ++n) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      s[n][e] = __expf(s[n][e] - mx0);
-      s[n][2 + e] = __expf(s[n][2 + e] - mx1);
+      s[n][e] = exp2f(s[n][e] - mx0);
+      s[n][2 + e] = exp2f(s[n][2 + e] - mx1);
       sum0 += s[n][e];
       sum1 += s[n][2 + e];
     }
@@ -130,88 +98,132 @@ __global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16))
   sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
   sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
   sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-  const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+  inv0 = 1.f / sum0;
+  inv1 = 1.f / sum1;
+}
+
+// Stage the [q|k|v] rows (and optionally dO) of one (group, head) into shared memory with 16-byte copies; the k-padding
+// columns DH..DHP-1 and the token-padding rows T..TP-1 are zero.
+template <int TP, int DH, int DHP, int LDQ, int NTHREADS, bool WITH_DO>
+__device__ __forceinline__ void stage_qkv(const bf16 *__restrict__ qkv, const bf16 *__restrict__ dout, bf16 *sQ, bf16 *sK, bf16 *sV,
+                                          bf16 *sdO, const int *rows, int T, int C, int head, int tid) {
+  constexpr int VPR = DH / 8, VPP = DHP / 8, NM = WITH_DO ? 4 : 3;
+  for (int idx = tid; idx < TP * NM * VPP; idx += NTHREADS) {
+    const int t = idx / (NM * VPP), rem = idx % (NM * VPP), which = rem / VPP, v8 = rem % VPP;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (t < T && v8 < VPR) {
+      if (which < 3)
+        val = *reinterpret_cast<const uint4 *>(qkv + (size_t)rows[t] * 3 * C + head * 3 * DH + which * DH + v8 * 8);
+      else
+        val = *reinterpret_cast<const uint4 *>(dout + (size_t)rows[t] * C + head * DH + v8 * 8);
+    }
+    bf16 *dst = which == 0 ? sQ : (which == 1 ? sK : (which == 2 ? sV : sdO));
+    *reinterpret_cast<uint4 *>(&dst[t * LDQ + v8 * 8]) = val;
+  }
+}
+
+// NT_S: 8-column tiles of the score matrix; NT_O: dh / 8; KS: ceil(dh / 16)
+template <int NT_S, int NT_O, int KS>
+__global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16))
+    attn_fwd_tc_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int H, int W, int C, int ph, int pw, int window,
+                       float scale) {
+  constexpr int TP = ((NT_S * 8 + 15) / 16) * 16;  // padded tokens
+  constexpr int DH = NT_O * 8, DHP = KS * 16;
+  constexpr int LDQ = DHP + 8;
+  constexpr int NTHREADS = 32 * (TP / 16);
+  __shared__ __align__(16) bf16 sQ[TP * LDQ];   // reused as the output staging tile
+  __shared__ __align__(16) bf16 sK[TP * LDQ];
+  __shared__ __align__(16) bf16 sV[TP * LDQ];
+  __shared__ int rows[TP];
+  const int T = ph * pw;
+  const int g = blockIdx.x, head = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = tid; t < TP; t += NTHREADS) rows[t] = t < T ? token_row(g, t, H, W, ph, pw, window) : 0;
+  __syncthreads();
+  stage_qkv<TP, DH, DHP, LDQ, NTHREADS, false>(qkv, nullptr, sQ, sK, sV, nullptr, rows, T, C, head, tid);
+  __syncthreads();
+  const int row0 = warp * 16;
+  float s[NT_S][4];
+#pragma unroll
+  for (int n = 0; n < NT_S; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    uint32_t a[4];
+    frag_a(a, sQ, LDQ, row0, ks * 16, lane);
+#pragma unroll
+    for (int n = 0; n < NT_S; ++n) {
+      uint32_t b0, b1;
+      frag_b(b0, b1, sK, LDQ, n * 8, ks * 16, lane);
+      mma16816(s[n], a, b0, b1);
+    }
+  }
+  const int tq = lane & 3, gq = lane >> 2;
+  float inv0, inv1;
+  softmax_rows<NT_S>(s, T, scale, tq, inv0, inv1);
   float o[NT_O][4];
 #pragma unroll
   for (int n = 0; n < NT_O; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 #pragma unroll
   for (int kk = 0; kk < TP / 16; ++kk) {
     uint32_t a[4];
+    a[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
+    a[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
     if (2 * kk + 1 < NT_S) {
-      a[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
-      a[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
       a[2] = pack2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
       a[3] = pack2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
     } else {
-      a[0] = pack2(s[2 * kk][0], s[2 * kk][1]);
-      a[1] = pack2(s[2 * kk][2], s[2 * kk][3]);
       a[2] = a[3] = 0u;
     }
 #pragma unroll
     for (int n = 0; n < NT_O; ++n) {
       uint32_t b0, b1;
-      load_b(b0, b1, sVt, LDT, n * 8, kk * 16, lane);
+      frag_b_t(b0, b1, sV, LDQ, n * 8, kk * 16, lane);   // V is [token][dh]: transposed load gives the [k=token][n=dh] operand
       mma16816(o[n], a, b0, b1);
     }
   }
-  const int gq = lane >> 2;
-  const int r0 = row0 + gq, r1 = row0 + gq + 8;
+  // stage the warp's 16 output rows in its own (now dead) slab of sQ, then write 16-byte pieces
+  __syncwarp();
 #pragma unroll
   for (int n = 0; n < NT_O; ++n) {
-    const int col = head * DH + n * 8 + 2 * tq;
-    if (r0 < T) *reinterpret_cast<uint32_t *>(out + (size_t)rows[r0] * C + col) = pack2(o[n][0] * inv0, o[n][1] * inv0);
-    if (r1 < T) *reinterpret_cast<uint32_t *>(out + (size_t)rows[r1] * C + col) = pack2(o[n][2] * inv1, o[n][3] * inv1);
+    *reinterpret_cast<uint32_t *>(&sQ[(row0 + gq) * LDQ + n * 8 + 2 * tq]) = pack2(o[n][0] * inv0, o[n][1] * inv0);
+    *reinterpret_cast<uint32_t *>(&sQ[(row0 + gq + 8) * LDQ + n * 8 + 2 * tq]) = pack2(o[n][2] * inv1, o[n][3] * inv1);
+  }
+  __syncwarp();
+  constexpr int VPR = DH / 8;
+  for (int idx = lane; idx < 16 * VPR; idx += 32) {
+    const int r = row0 + idx / VPR, v8 = idx % VPR;
+    if (r < T) *reinterpret_cast<uint4 *>(out + (size_t)rows[r] * C + head * DH + v8 * 8) = *reinterpret_cast<const uint4 *>(&sQ[r * LDQ + v8 * 8]);
   }
 }
 
-// Backward: recompute P, dP = dO V^T, dS = P o (dP - rowsum(P o dP)); then dQ = dS K, dK = dS^T Q,
-// dV = P^T dO with the transposed operands staged in shared memory.
+// Backward: recompute P, dP = dO V^T, dS = P o (dP - rowsum(P o dP)) * scale; dQ = dS K from registers; P and dS go
+// to shared memory once and dK = dS^T Q, dV = P^T dO read them (and Q, dO) through transposing ldmatrix loads.
 template <int NT_S, int NT_O, int KS>
-__global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16))
+__global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16), 3)
     attn_bwd_tc_kernel(const bf16 *__restrict__ qkv, const bf16 *__restrict__ dout, bf16 *__restrict__ dqkv, int H, int W, int C,
                        int ph, int pw, int window, float scale) {
   constexpr int TP = ((NT_S * 8 + 15) / 16) * 16;
   constexpr int DH = NT_O * 8, DHP = KS * 16;
-  constexpr int LDQ = DHP + 8, LDT = TP + 8;
+  constexpr int LDQ = DHP + 8, LDT = TP + 8, LDO = 3 * DH + 8;
   constexpr int NTHREADS = 32 * (TP / 16);
   extern __shared__ __align__(16) uint8_t smem_dyn[];
   bf16 *sQ = reinterpret_cast<bf16 *>(smem_dyn);     // [TP][LDQ]
-  bf16 *sK = sQ + TP * LDQ;                          // [TP][LDQ]
-  bf16 *sV = sK + TP * LDQ;                          // [TP][LDQ]
-  bf16 *sdO = sV + TP * LDQ;                         // [TP][LDQ]
-  bf16 *sQt = sdO + TP * LDQ;                        // [DH][LDT]
-  bf16 *sKt = sQt + DH * LDT;                        // [DH][LDT]
-  bf16 *sdOt = sKt + DH * LDT;                       // [DH][LDT]
-  bf16 *sdS = sdOt + DH * LDT;                       // [TP][LDT]
-  bf16 *sdSt = sdS + TP * LDT;                       // [TP][LDT]
-  bf16 *sPt = sdSt + TP * LDT;                       // [TP][LDT]
-  int *rows = reinterpret_cast<int *>(sPt + TP * LDT);
-  constexpr int TOTAL_BF16 = 4 * TP * LDQ + 3 * DH * LDT + 3 * TP * LDT;
+  bf16 *sK = sQ + TP * LDQ;
+  bf16 *sV = sK + TP * LDQ;
+  bf16 *sdO = sV + TP * LDQ;
+  bf16 *sdS = sdO + TP * LDQ;                        // [TP][LDT]  (rows = queries)
+  bf16 *sP = sdS + TP * LDT;                         // [TP][LDT]
+  int *rows = reinterpret_cast<int *>(sP + TP * LDT);
+  bf16 *sOut = sdS;                                  // [TP][LDO] output staging, aliases sdS/sP after the last read
+  static_assert(TP * LDO <= 2 * TP * LDT, "output staging must fit");
   const int T = ph * pw;
   const int g = blockIdx.x, head = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < TOTAL_BF16 / 2; i += NTHREADS) reinterpret_cast<uint32_t *>(smem_dyn)[i] = 0u;
   for (int t = tid; t < TP; t += NTHREADS) rows[t] = t < T ? token_row(g, t, H, W, ph, pw, window) : 0;
   __syncthreads();
-  constexpr int VPR = DH / 8;
-  for (int idx = tid; idx < T * 4 * VPR; idx += NTHREADS) {
-    const int t = idx / (4 * VPR), rem = idx % (4 * VPR), which = rem / VPR, v8 = rem % VPR;
-    uint4 val;
-    if (which < 3)
-      val = *reinterpret_cast<const uint4 *>(qkv + (size_t)rows[t] * 3 * C + head * 3 * DH + which * DH + v8 * 8);
-    else
-      val = *reinterpret_cast<const uint4 *>(dout + (size_t)rows[t] * C + head * DH + v8 * 8);
-    bf16 *dst = which == 0 ? sQ : (which == 1 ? sK : (which == 2 ? sV : sdO));
-    *reinterpret_cast<uint4 *>(&dst[t * LDQ + v8 * 8]) = val;
-    bf16 *dstT = which == 0 ? sQt : (which == 1 ? sKt : (which == 3 ? sdOt : nullptr));
-    if (dstT) {
-      const bf16 *e = reinterpret_cast<const bf16 *>(&val);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dstT[(v8 * 8 + j) * LDT + t] = e[j];
-    }
-  }
+  stage_qkv<TP, DH, DHP, LDQ, NTHREADS, true>(qkv, dout, sQ, sK, sV, sdO, rows, T, C, head, tid);
   __syncthreads();
   const int row0 = warp * 16;
   const int tq = lane & 3, gq = lane >> 2;
+  float dq[NT_O][4];
   {
     float s[NT_S][4], dp[NT_S][4];
 #pragma unroll
@@ -222,49 +234,19 @@ __global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16))
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       uint32_t a[4], ad[4];
-      load_a(a, sQ, LDQ, row0, ks * 16, lane);
-      load_a(ad, sdO, LDQ, row0, ks * 16, lane);
+      frag_a(a, sQ, LDQ, row0, ks * 16, lane);
+      frag_a(ad, sdO, LDQ, row0, ks * 16, lane);
 #pragma unroll
       for (int n = 0; n < NT_S; ++n) {
         uint32_t b0, b1;
-        load_b(b0, b1, sK, LDQ, n * 8, ks * 16, lane);
+        frag_b(b0, b1, sK, LDQ, n * 8, ks * 16, lane);
         mma16816(s[n], a, b0, b1);
-        load_b(b0, b1, sV, LDQ, n * 8, ks * 16, lane);
+        frag_b(b0, b1, sV, LDQ, n * 8, ks * 16, lane);
         mma16816(dp[n], ad, b0, b1);
       }
     }
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int n = 0; n < NT_S; ++n) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool ok = n * 8 + 2 * tq + e < T;
-        s[n][e] = ok ? s[n][e] * scale : -INFINITY;
-        s[n][2 + e] = ok ? s[n][2 + e] * scale : -INFINITY;
-        mx0 = fmaxf(mx0, s[n][e]);
-        mx1 = fmaxf(mx1, s[n][2 + e]);
-      }
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-    for (int n = 0; n < NT_S; ++n) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        s[n][e] = __expf(s[n][e] - mx0);
-        s[n][2 + e] = __expf(s[n][2 + e] - mx1);
-        sum0 += s[n][e];
-        sum1 += s[n][2 + e];
-      }
-    }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    float inv0, inv1;
+    softmax_rows<NT_S>(s, T, scale, tq, inv0, inv1);
     float d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int n = 0; n < NT_S; ++n) {
@@ -280,68 +262,89 @@ __global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16))
     d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
     d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-    const int r0 = row0 + gq, r1 = row0 + gq + 8;
+    // P and dS: packed to bf16 once; to shared memory (for dK / dV) and kept as A fragments (for dQ)
+    uint32_t ds_lo[NT_S], ds_hi[NT_S];
 #pragma unroll
     for (int n = 0; n < NT_S; ++n) {
+      ds_lo[n] = pack2(s[n][0] * (dp[n][0] - d0) * scale, s[n][1] * (dp[n][1] - d0) * scale);
+      ds_hi[n] = pack2(s[n][2] * (dp[n][2] - d1) * scale, s[n][3] * (dp[n][3] - d1) * scale);
+      const int col = n * 8 + 2 * tq;
+      *reinterpret_cast<uint32_t *>(&sdS[(row0 + gq) * LDT + col]) = ds_lo[n];
+      *reinterpret_cast<uint32_t *>(&sdS[(row0 + gq + 8) * LDT + col]) = ds_hi[n];
+      *reinterpret_cast<uint32_t *>(&sP[(row0 + gq) * LDT + col]) = pack2(s[n][0], s[n][1]);
+      *reinterpret_cast<uint32_t *>(&sP[(row0 + gq + 8) * LDT + col]) = pack2(s[n][2], s[n][3]);
+    }
+    if (NT_S * 8 < TP) {   // zero the token-padding columns (they are read as the k dimension below)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = n * 8 + 2 * tq + e;
-        if (col < TP) {
-          const float p0 = s[n][e], p1 = s[n][2 + e];
-          const bf16 ds0 = __float2bfloat16_rn(p0 * (dp[n][e] - d0) * scale);
-          const bf16 ds1 = __float2bfloat16_rn(p1 * (dp[n][2 + e] - d1) * scale);
-          sdS[r0 * LDT + col] = ds0;
-          sdS[r1 * LDT + col] = ds1;
-          sdSt[col * LDT + r0] = ds0;
-          sdSt[col * LDT + r1] = ds1;
-          sPt[col * LDT + r0] = __float2bfloat16_rn(p0);
-          sPt[col * LDT + r1] = __float2bfloat16_rn(p1);
-        }
+      for (int c = NT_S * 8 + 2 * tq; c < TP; c += 8) {
+        *reinterpret_cast<uint32_t *>(&sdS[(row0 + gq) * LDT + c]) = 0u;
+        *reinterpret_cast<uint32_t *>(&sdS[(row0 + gq + 8) * LDT + c]) = 0u;
+        *reinterpret_cast<uint32_t *>(&sP[(row0 + gq) * LDT + c]) = 0u;
+        *reinterpret_cast<uint32_t *>(&sP[(row0 + gq + 8) * LDT + c]) = 0u;
+      }
+    }
+    // dQ = dS K  (k = key tokens, n = dh): K is [token][dh] -> transposed B loads
+#pragma unroll
+    for (int n = 0; n < NT_O; ++n) dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < TP / 16; ++kk) {
+      uint32_t a[4];
+      a[0] = ds_lo[2 * kk];
+      a[1] = ds_hi[2 * kk];
+      if (2 * kk + 1 < NT_S) {
+        a[2] = ds_lo[2 * kk + 1];
+        a[3] = ds_hi[2 * kk + 1];
+      } else {
+        a[2] = a[3] = 0u;
+      }
+#pragma unroll
+      for (int n = 0; n < NT_O; ++n) {
+        uint32_t b0, b1;
+        frag_b_t(b0, b1, sK, LDQ, n * 8, kk * 16, lane);
+        mma16816(dq[n], a, b0, b1);
       }
     }
   }
   __syncthreads();
-  // second phase: this warp's 16 rows of dQ (rows = queries) and of dK, dV (rows = keys)
-  float dq[NT_O][4], dk[NT_O][4], dv[NT_O][4];
+  // this warp's 16 KEY rows of dK = dS^T Q and dV = P^T dO  (k = query tokens)
+  float dk[NT_O][4], dv[NT_O][4];
 #pragma unroll
   for (int n = 0; n < NT_O; ++n) {
-    dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f;
     dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f;
     dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f;
   }
 #pragma unroll
   for (int kk = 0; kk < TP / 16; ++kk) {
-    uint32_t a1[4], a2[4], a3[4];
-    load_a(a1, sdS, LDT, row0, kk * 16, lane);
-    load_a(a2, sdSt, LDT, row0, kk * 16, lane);
-    load_a(a3, sPt, LDT, row0, kk * 16, lane);
+    uint32_t a2[4], a3[4];
+    frag_a_t(a2, sdS, LDT, row0, kk * 16, lane);
+    frag_a_t(a3, sP, LDT, row0, kk * 16, lane);
 #pragma unroll
     for (int n = 0; n < NT_O; ++n) {
       uint32_t b0, b1;
-      load_b(b0, b1, sKt, LDT, n * 8, kk * 16, lane);
-      mma16816(dq[n], a1, b0, b1);
-      load_b(b0, b1, sQt, LDT, n * 8, kk * 16, lane);
+      frag_b_t(b0, b1, sQ, LDQ, n * 8, kk * 16, lane);
       mma16816(dk[n], a2, b0, b1);
-      load_b(b0, b1, sdOt, LDT, n * 8, kk * 16, lane);
+      frag_b_t(b0, b1, sdO, LDQ, n * 8, kk * 16, lane);
       mma16816(dv[n], a3, b0, b1);
     }
   }
-  const int r0 = row0 + gq, r1 = row0 + gq + 8;
+  __syncthreads();   // every warp is done reading sdS / sP: reuse them as the [token][dq|dk|dv] staging tile
 #pragma unroll
   for (int n = 0; n < NT_O; ++n) {
-    const int col = head * 3 * DH + n * 8 + 2 * tq;
-    if (r0 < T) {
-      bf16 *dst = dqkv + (size_t)rows[r0] * 3 * C + col;
-      *reinterpret_cast<uint32_t *>(dst) = pack2(dq[n][0], dq[n][1]);
-      *reinterpret_cast<uint32_t *>(dst + DH) = pack2(dk[n][0], dk[n][1]);
-      *reinterpret_cast<uint32_t *>(dst + 2 * DH) = pack2(dv[n][0], dv[n][1]);
-    }
-    if (r1 < T) {
-      bf16 *dst = dqkv + (size_t)rows[r1] * 3 * C + col;
-      *reinterpret_cast<uint32_t *>(dst) = pack2(dq[n][2], dq[n][3]);
-      *reinterpret_cast<uint32_t *>(dst + DH) = pack2(dk[n][2], dk[n][3]);
-      *reinterpret_cast<uint32_t *>(dst + 2 * DH) = pack2(dv[n][2], dv[n][3]);
-    }
+    const int col = n * 8 + 2 * tq;
+    bf16 *r0p = sOut + (row0 + gq) * LDO + col, *r1p = sOut + (row0 + gq + 8) * LDO + col;
+    *reinterpret_cast<uint32_t *>(r0p) = pack2(dq[n][0], dq[n][1]);
+    *reinterpret_cast<uint32_t *>(r1p) = pack2(dq[n][2], dq[n][3]);
+    *reinterpret_cast<uint32_t *>(r0p + DH) = pack2(dk[n][0], dk[n][1]);
+    *reinterpret_cast<uint32_t *>(r1p + DH) = pack2(dk[n][2], dk[n][3]);
+    *reinterpret_cast<uint32_t *>(r0p + 2 * DH) = pack2(dv[n][0], dv[n][1]);
+    *reinterpret_cast<uint32_t *>(r1p + 2 * DH) = pack2(dv[n][2], dv[n][3]);
+  }
+  __syncwarp();
+  constexpr int VPO = 3 * DH / 8;   // 16-byte pieces per token: the head's [dq|dk|dv] block is contiguous in dqkv
+  for (int idx = lane; idx < 16 * VPO; idx += 32) {
+    const int r = row0 + idx / VPO, v8 = idx % VPO;
+    if (r < T)
+      *reinterpret_cast<uint4 *>(dqkv + (size_t)rows[r] * 3 * C + head * 3 * DH + v8 * 8) = *reinterpret_cast<const uint4 *>(&sOut[r * LDO + v8 * 8]);
   }
 }
 
@@ -356,8 +359,8 @@ template <int NT_S, int NT_O, int KS>
 int launch_bwd(const bf16 *qkv, const bf16 *dout, bf16 *dqkv, int groups, int heads, int H, int W, int C, int ph, int pw, int window,
                float scale, cudaStream_t st) {
   constexpr int TP = ((NT_S * 8 + 15) / 16) * 16;
-  constexpr int DH = NT_O * 8, DHP = KS * 16, LDQ = DHP + 8, LDT = TP + 8;
-  constexpr size_t smem = 2 * (4 * TP * LDQ + 3 * DH * LDT + 3 * TP * LDT) + 4 * TP;
+  constexpr int DHP = KS * 16, LDQ = DHP + 8, LDT = TP + 8;
+  constexpr size_t smem = 2 * (4 * TP * LDQ + 2 * TP * LDT) + 4 * TP;
   static bool set = false;
   if (!set) {
     LEOD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<NT_S, NT_O, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
