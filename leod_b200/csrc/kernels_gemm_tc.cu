@@ -128,8 +128,10 @@ struct NtArgs {
   int staged;     // epilogue writes through shared memory (N multiple of 16: every chunk is full)
 };
 
-constexpr int NT_EPI_WARPS = 8;
-constexpr int NT_THREADS = 64 + 32 * NT_EPI_WARPS;
+// epilogue warps: a multiple of 4 (one TMEM lane quarter each); the column range of a tile is split between the warps that
+// share a quarter.  The GELU epilogues are instruction-bound (erf + two outputs), so they get more warps.
+template <int EPI> struct NtEpiWarps { static constexpr int value = (EPI == EPI_GELU || EPI == EPI_GELU_BWD) ? 12 : 8; };
+template <int EPI> struct NtStageBytes { static constexpr int value = EPI == EPI_GELU ? 8192 : 4096; };   // per epilogue warp
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -316,7 +318,7 @@ __device__ __forceinline__ void nt_flush_stage(const uint8_t *stage, bf16 *dst, 
 // so the MMAs of tile j+1 overlap the epilogue of tile j, and eight epilogue warps (two per TMEM lane quarter, each
 // taking half of the columns) drain it.
 template <int EPI>   // EPI_* : staged epilogue specialised for that mode;  -1 : generic per-thread stores (ragged N)
-__global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                     const __grid_constant__ CUtensorMap mapA2,
                                                                     const __grid_constant__ CUtensorMap mapB,
                                                                     const __grid_constant__ CUtensorMap mapB2, const NtArgs a) {
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc_kernel(const __grid_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tmem_full[b]), 1);
-      mbar_init(smem_u32(&tmem_empty[b]), NT_EPI_WARPS);
+      mbar_init(smem_u32(&tmem_empty[b]), NtEpiWarps<EPI>::value);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -403,10 +405,11 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       }
     }
   } else {
-    // epilogue: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4, one accumulator row per thread
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    // epilogue: TMEM lane quarter = warp % 4 (hardware rule), column part = (warp - 2) / 4, one accumulator row per thread
+    constexpr int CS = NtEpiWarps<EPI>::value / 4;
+    const int quarter = warp & 3, part = (warp - 2) >> 2;
     const int nchunks = a.BN >> 4;
-    const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2, c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
+    const int c_begin = (nchunks * part) / CS, c_end = (nchunks * (part + 1)) / CS;
     const GemmNT &g = a.g;
     int j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(NT_THREADS, 1) gemm_nt_tc_kernel(const __grid_
       uint32_t rbuf[2][16];
       if (c_begin < c_end) tmem_ld16_async(trow + (uint32_t)(c_begin * 16), rbuf[0]);
       if (EPI >= 0) {
-        uint8_t *stC = stage_base + (warp - 2) * 8192, *stT = stC + 4096;
+        uint8_t *stC = stage_base + (warp - 2) * NtStageBytes<EPI>::value, *stT = stC + 4096;
         const int m_base = m0 + quarter * 32;
         int gs = c_begin;   // first chunk of the current group of <= 4 chunks
 #pragma unroll 1
@@ -760,7 +763,9 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   const int stage_bytes = A_STAGE_BYTES + a.BN * TILE_K * 2;
   const int total_kb = a.nkb * ceil_div(a.tiles_m * a.tiles_n, num_sms());
   a.staged = (g.N % 16 == 0 && (((uintptr_t)g.bias) & 15) == 0) ? 1 : 0;
-  const int epi_bytes = NT_EPI_WARPS * 8192 + 256;
+  const bool gelu_like = a.staged && (g.epi == EPI_GELU || g.epi == EPI_GELU_BWD);
+  const int epi_warps = gelu_like ? NtEpiWarps<EPI_GELU>::value : 8;
+  const int epi_bytes = epi_warps * ((a.staged && g.epi == EPI_GELU) ? 8192 : 4096) + 256;
   a.stages = std::min(std::min(4, (int)((224 * 1024 - epi_bytes - 2048) / stage_bytes)), std::max(total_kb, 1));
   CUtensorMap mA, mA2, mB, mB2;
   LEOD_TRY(make_map(&mA, g.A, K1, g.M, g.lda, TILE_K, TILE_M));
@@ -786,16 +791,17 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   const int tiles = a.tiles_m * a.tiles_n;
   const int waves = ceil_div(tiles, num_sms());
   const int grid = ceil_div(tiles, waves);
+  const int threads = 64 + 32 * epi_warps;
   if (!a.staged) {
-    gemm_nt_tc_kernel<-1><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+    gemm_nt_tc_kernel<-1><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
   } else if (g.epi == EPI_GELU) {
-    gemm_nt_tc_kernel<EPI_GELU><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+    gemm_nt_tc_kernel<EPI_GELU><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
   } else if (g.epi == EPI_RESID) {
-    gemm_nt_tc_kernel<EPI_RESID><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+    gemm_nt_tc_kernel<EPI_RESID><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
   } else if (g.epi == EPI_GELU_BWD) {
-    gemm_nt_tc_kernel<EPI_GELU_BWD><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+    gemm_nt_tc_kernel<EPI_GELU_BWD><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
   } else {
-    gemm_nt_tc_kernel<EPI_NONE><<<grid, NT_THREADS, smem, st>>>(mA, mA2, mB, mB2, a);
+    gemm_nt_tc_kernel<EPI_NONE><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
   }
   LEOD_LAUNCH_CHECK();
   return 0;
