@@ -78,7 +78,9 @@ struct leod_backbone {
   void *seq_arena = nullptr;
   void *seq_col0 = nullptr;      // stem patch matrix of the whole window [L*B*Ho*Wo, Kp] (kept from forward to backward)
   int64_t seq_col0_imgs = 0;
-  bool col0_live = false;        // set for the duration of a sequence-mode forward/backward pair
+  bool col0_live = false;
+  unsigned *seq_flags = nullptr;  // per-(tile, timestep) arrival counters of the fused recurrence kernels
+  int fused_lstm = 1;        // set for the duration of a sequence-mode forward/backward pair
   size_t esz() const { return cfg.dtype == LEOD_BF16 ? 2 : 4; }
   int gemm_impl = 0;  // 0 SIMT, 1 tensor core (bf16 only)
 };
@@ -550,6 +552,7 @@ extern "C" void leod_backbone_destroy(leod_backbone_t *h) {
   free_workspace(h);
   if (h->seq_arena) cudaFree(h->seq_arena);
   if (h->seq_col0) cudaFree(h->seq_col0);
+  if (h->seq_flags) cudaFree(h->seq_flags);
   delete h;
 }
 
@@ -683,7 +686,10 @@ static int ensure_seq(leod_backbone *h, int B, int L) {
   if (h->seq_arena && h->seq_B == B && h->seq_L == L) return 0;
   if (h->seq_arena) cudaFree(h->seq_arena);
   if (h->seq_col0) cudaFree(h->seq_col0);
+  if (h->seq_flags) cudaFree(h->seq_flags);
   h->seq_arena = h->seq_col0 = nullptr;
+  h->seq_flags = nullptr;
+  LEOD_CUDA(cudaMalloc((void **)&h->seq_flags, sizeof(unsigned) * (size_t)(((int64_t)B * h->d[0].Ho * h->d[0].Wo + 127) / 128) * L));
   h->seq_col0_imgs = 0;
   StageLayout lay[4];
   int64_t n;
@@ -739,14 +745,21 @@ extern "C" int leod_backbone_seq_fwd(leod_backbone_t *h, const void *x, int x_dt
                            h->params + h->p[s].lstmb), st));
     char *hs = (char *)h_all[s];
     char *cs = (char *)h->seq_arena + lay[s].c_all * e;
-    for (int t = 0; t < L; ++t) {
-      const void *hp = t == 0 ? (h0 ? h0[s] : nullptr) : hs + (t - 1) * M * C * e;
-      const void *cp = t == 0 ? (c0 ? c0[s] : nullptr) : cs + (t - 1) * M * C * e;
-      void *gt = (char *)b.gates + t * M * 4 * C * e;
-      if (hp)  // gates_t += h_{t-1} W_h^T (in place: every element is read and written by the same thread)
-        LEOD_TRY(gemm_nt(h, mk(hp, (int)C, eoff(h, h->w[s].Wl, C), (int)(2 * C), gt, (int)(4 * C), (int)M, (int)(4 * C), (int)C, nullptr,
-                               EPI_RESID, gt, (int)(4 * C)), st));
-      LEOD_TRY(lstm_pointwise_fwd(h->cfg.dtype, gt, cp, hs + t * M * C * e, cs + t * M * C * e, (int)M, (int)C, st));
+    if (h->cfg.dtype == LEOD_BF16 && h->gemm_impl == 1 && h->fused_lstm && C % 16 == 0) {
+      // the whole recurrence of this stage in one launch (kernels_gemm_tc.cu, lstm_seq_fwd_kernel)
+      ProfScope ps(PK_LSTM, 2.0 * M * L * 4 * C * C + 30.0 * M * L * C, 11.0 * M * L * C * e, st, (int)M, (int)C, L);
+      LEOD_TRY(lstm_seq_fwd_tc(b.gates, eoff(h, h->w[s].Wl, C), (int)(2 * C), h0 ? h0[s] : nullptr, c0 ? c0[s] : nullptr, hs, cs,
+                               h->seq_flags, (int)M, (int)C, L, st));
+    } else {
+      for (int t = 0; t < L; ++t) {
+        const void *hp = t == 0 ? (h0 ? h0[s] : nullptr) : hs + (t - 1) * M * C * e;
+        const void *cp = t == 0 ? (c0 ? c0[s] : nullptr) : cs + (t - 1) * M * C * e;
+        void *gt = (char *)b.gates + t * M * 4 * C * e;
+        if (hp)  // gates_t += h_{t-1} W_h^T (in place: every element is read and written by the same thread)
+          LEOD_TRY(gemm_nt(h, mk(hp, (int)C, eoff(h, h->w[s].Wl, C), (int)(2 * C), gt, (int)(4 * C), (int)M, (int)(4 * C), (int)C, nullptr,
+                                 EPI_RESID, gt, (int)(4 * C)), st));
+        LEOD_TRY(lstm_pointwise_fwd(h->cfg.dtype, gt, cp, hs + t * M * C * e, cs + t * M * C * e, (int)M, (int)C, st));
+      }
     }
   }
   for (int s = 0; s < 4; ++s) {

@@ -104,6 +104,8 @@ int gemm_tn_simt(int dtype, const void *dY, int ldy, const void *X, int ldx, flo
 int gemm_nt_tc(const GemmNT &g, cudaStream_t st);
 int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N, int K,
                cudaStream_t st);
+int lstm_seq_fwd_tc(void *gates, const void *Wh, int ldw, const void *h0, const void *c0, void *h_all, void *c_all, unsigned *flags,
+                    int M, int C, int L, cudaStream_t st);
 // kernels_attention.cu
 int attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, int C, int dh, int ph, int pw, int window,
                   cudaStream_t st);

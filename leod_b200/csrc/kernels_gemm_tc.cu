@@ -731,6 +731,315 @@ __global__ void colsum_bf16_slow_kernel(const bf16 *__restrict__ Y, int ldy, flo
   for (int m = m0; m < m1; ++m) acc += __bfloat162float(Y[(size_t)m * ldy + n]);
   atomicAdd(&out[n], acc);
 }
+
+// ============================================================================================ fused ConvLSTM recurrence
+// One launch runs ALL L timesteps of a stage's recurrence (models/layers/rnn.py:53-68 with the input half of the gates
+// precomputed):   gates_t = Gx_t + h_{t-1} W_h^T ;  f,i,o = sigmoid, g = tanh ;  c_t = f c_{t-1} + i g ;  h_t = o tanh(c_t).
+// The "conv" is 1x1, so token rows are independent: a CTA owns 128-token tiles and walks them through time.  h_t is
+// written to global memory (it is an output anyway) and comes back as the next step's A operand through TMA; a
+// per-(tile, t) arrival counter in global memory orders the two (generic-proxy stores -> fence.proxy.async -> release
+// add; acquire load -> TMA).  Wide stages (4C > 256 accumulator columns) run in passes of CW channels x 4 gates; when
+// tiles x passes fits on the GPU every (tile, pass) gets its own CTA and the counters also synchronise the passes.
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = gate math (one TMEM lane quarter each).  The gate-math warps move
+// Gx / c / h / activated gates through swizzled shared-memory staging so every global access is a 128-byte row segment.
+struct LstmSeqArgs {
+  bf16 *gates;          // [L][M][4C]  in: x-half pre-activations (+bias); out: activated gates (f|i|o|g)
+  const bf16 *c0;       // [M][C] or null
+  bf16 *h_all, *c_all;  // [L][M][C]
+  unsigned *flags;      // [tiles_m][L] arrival counters, zero on entry
+  int M, C, L, CW, npass, split, has_h0, nkb, stages, tiles_m;
+};
+constexpr int LS_THREADS = 192;
+constexpr int LS_WARP_STAGE = 4 * 4096 + 4096 + 4096;   // per gate-math warp: gates [4][32 rows][128 B], c, h
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+__global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap mapH,   // h_all [C, M, L]
+                                                                      const __grid_constant__ CUtensorMap mapH0,  // h0 [C, M, 1]
+                                                                      const __grid_constant__ CUtensorMap mapW,   // W_h [C, 4C]
+                                                                      const LstmSeqArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_stage_bytes = 4 * a.CW * TILE_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint8_t *stage_base = smem + (size_t)a.stages * stage_bytes;          // 4 x LS_WARP_STAGE, 1024-aligned
+  uint64_t *bars = (uint64_t *)(stage_base + 4 * LS_WARP_STAGE);
+  uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages, *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int acc_cols = 4 * a.CW;               // <= 256
+  const int C = a.C, M = a.M;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_empty[b]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work list of this CTA: split -> one (tile, pass); otherwise tiles blockIdx.x, +gridDim.x, ... with all passes
+  const int tile_first = a.split ? (int)blockIdx.x / a.npass : (int)blockIdx.x;
+  const int tile_step = a.split ? a.tiles_m : (int)gridDim.x;       // split: exactly one tile
+  const int pass_first = a.split ? (int)blockIdx.x % a.npass : 0;
+  const int pass_count = a.split ? 1 : a.npass;
+  const unsigned flag_target = 4u * (unsigned)a.npass;              // 4 gate-math warps per (tile, pass)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = 0; t < a.L; ++t) {
+        if (t == 0 && !a.has_h0) continue;
+        for (int tile = tile_first; tile < a.tiles_m; tile += tile_step) {
+          if (t > 0) {   // h_{t-1} of this tile must be complete (all passes) and visible to the async proxy
+            const unsigned *f = a.flags + (size_t)tile * a.L + (t - 1);
+            unsigned v;
+            const long long t0 = clock64();
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+              if (v < flag_target && clock64() - t0 > 20000000000LL) __trap();
+            } while (v < flag_target);
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          for (int p = 0; p < pass_count; ++p) {
+            const int pass = pass_first + p;
+            for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+              const int s = it % a.stages;
+              const uint32_t ph = (it / a.stages) & 1;
+              mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+              const uint32_t fb = smem_u32(&full_bar[s]);
+              mbar_expect_tx(fb, stage_bytes);
+              const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
+              if (t > 0) tma_load_3d(sa, &mapH, fb, kb * TILE_K, tile * TILE_M, t - 1);
+              else tma_load_3d(sa, &mapH0, fb, kb * TILE_K, tile * TILE_M, 0);
+              for (int g = 0; g < 4; ++g)
+                tma_load_2d(sb + g * a.CW * TILE_K * 2, &mapW, fb, kb * TILE_K, g * C + pass * a.CW);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TILE_M, acc_cols, 0, 0);
+      int it = 0, j = 0;
+      for (int t = 0; t < a.L; ++t) {
+        if (t == 0 && !a.has_h0) continue;
+        for (int tile = tile_first; tile < a.tiles_m; tile += tile_step) {
+          for (int p = 0; p < pass_count; ++p, ++j) {
+            const int buf = j & 1;
+            mbar_wait(smem_u32(&tmem_empty[buf]), ((j >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+            for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+              const int s = it % a.stages;
+              const uint32_t ph = (it / a.stages) & 1;
+              mbar_wait(smem_u32(&full_bar[s]), ph);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
+              const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < TILE_K / 16; ++k) tc_mma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              tc_commit(smem_u32(&empty_bar[s]));
+            }
+            tc_commit(smem_u32(&tmem_full[buf]));
+          }
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    uint8_t *stG = stage_base + (warp - 2) * LS_WARP_STAGE, *stC = stG + 4 * 4096, *stH = stC + 4096;
+    const int ppr = a.CW >> 3;                    // 16-byte pieces per row segment (6 or 8)
+    const int pieces = 32 * ppr;
+    const int nchunk = a.CW >> 4;                 // 16-channel chunks per pass
+    int j = 0;
+    for (int t = 0; t < a.L; ++t) {
+      const bool mma = !(t == 0 && !a.has_h0);
+      for (int tile = tile_first; tile < a.tiles_m; tile += tile_step) {
+        const int m_base = tile * TILE_M + quarter * 32;
+        for (int p = 0; p < pass_count; ++p) {
+          const int pass = pass_first + p;
+          const int ch0 = pass * a.CW;
+          // ---- stage Gx (4 gates) and c_{t-1}: coalesced 16-byte async copies into the swizzled tiles
+          for (int q = lane; q < pieces; q += 32) {
+            const int row = q / ppr, c16 = q - row * ppr;
+            const int m = m_base + row;
+            const bool ok = m < M;
+            const uint32_t off = row * 128 + ((c16 ^ (row & 7)) << 4);
+            const bf16 *gsrc = a.gates + ((size_t)t * M + (ok ? m : 0)) * 4 * C + ch0 + c16 * 8;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) cp_async16(smem_u32(stG + g * 4096 + off), gsrc + (size_t)g * C, ok);
+            const bf16 *cprev = t > 0 ? a.c_all + ((size_t)(t - 1) * M + (ok ? m : 0)) * C + ch0 + c16 * 8
+                                      : (a.c0 ? a.c0 + (size_t)(ok ? m : 0) * C + ch0 + c16 * 8 : nullptr);
+            cp_async16(smem_u32(stC + off), cprev ? (const void *)cprev : (const void *)a.gates, ok && cprev != nullptr);
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          int buf = 0;
+          if (mma) {
+            buf = j & 1;
+            mbar_wait(smem_u32(&tmem_full[buf]), (j >> 1) & 1);
+            tc_fence_after();
+          }
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256);
+          const uint32_t rowoff = lane * 128;
+          const int sw = lane & 7;
+          for (int cc = 0; cc < nchunk; ++cc) {
+            float pre[4][16];
+            if (mma) {
+              uint32_t r[4][16];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tmem_ld16_async(trow + (uint32_t)(g * a.CW + cc * 16), r[g]);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                tmem_ld_wait(r[g]);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pre[g][e] = __uint_as_float(r[g][e]);
+              }
+            } else {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pre[g][e] = 0.f;
+            }
+            const uint32_t o0 = rowoff + (((2 * cc) ^ sw) << 4), o1 = rowoff + (((2 * cc + 1) ^ sw) << 4);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint4 x0 = *reinterpret_cast<const uint4 *>(stG + g * 4096 + o0), x1 = *reinterpret_cast<const uint4 *>(stG + g * 4096 + o1);
+              const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                pre[g][2 * e] += __uint_as_float(w[e] << 16);
+                pre[g][2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+              }
+            }
+            float cp[16];
+            {
+              const uint4 x0 = *reinterpret_cast<const uint4 *>(stC + o0), x1 = *reinterpret_cast<const uint4 *>(stC + o1);
+              const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                cp[2 * e] = __uint_as_float(w[e] << 16);
+                cp[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+              }
+            }
+            uint32_t og[4][8], oc[8], oh[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float f[2], ig[2], o[2], gg[2], cn[2], hn[2];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                f[u] = sigmoid_fast(pre[0][2 * e + u]);
+                ig[u] = sigmoid_fast(pre[1][2 * e + u]);
+                o[u] = sigmoid_fast(pre[2][2 * e + u]);
+                gg[u] = tanh_fast(pre[3][2 * e + u]);
+                cn[u] = fmaf(f[u], cp[2 * e + u], ig[u] * gg[u]);
+                hn[u] = o[u] * tanh_fast(cn[u]);
+              }
+              __nv_bfloat162 v;
+              v = __floats2bfloat162_rn(f[0], f[1]); og[0][e] = *reinterpret_cast<uint32_t *>(&v);
+              v = __floats2bfloat162_rn(ig[0], ig[1]); og[1][e] = *reinterpret_cast<uint32_t *>(&v);
+              v = __floats2bfloat162_rn(o[0], o[1]); og[2][e] = *reinterpret_cast<uint32_t *>(&v);
+              v = __floats2bfloat162_rn(gg[0], gg[1]); og[3][e] = *reinterpret_cast<uint32_t *>(&v);
+              v = __floats2bfloat162_rn(cn[0], cn[1]); oc[e] = *reinterpret_cast<uint32_t *>(&v);
+              v = __floats2bfloat162_rn(hn[0], hn[1]); oh[e] = *reinterpret_cast<uint32_t *>(&v);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              *reinterpret_cast<uint4 *>(stG + g * 4096 + o0) = make_uint4(og[g][0], og[g][1], og[g][2], og[g][3]);
+              *reinterpret_cast<uint4 *>(stG + g * 4096 + o1) = make_uint4(og[g][4], og[g][5], og[g][6], og[g][7]);
+            }
+            *reinterpret_cast<uint4 *>(stC + o0) = make_uint4(oc[0], oc[1], oc[2], oc[3]);
+            *reinterpret_cast<uint4 *>(stC + o1) = make_uint4(oc[4], oc[5], oc[6], oc[7]);
+            *reinterpret_cast<uint4 *>(stH + o0) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            *reinterpret_cast<uint4 *>(stH + o1) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+          }
+          if (mma) {   // accumulator drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
+            ++j;
+          } else {
+            __syncwarp();
+          }
+          // ---- write activated gates, c_t, h_t as 16-byte pieces of contiguous row segments
+          for (int q = lane; q < pieces; q += 32) {
+            const int row = q / ppr, c16 = q - row * ppr;
+            const int m = m_base + row;
+            if (m < M) {
+              const uint32_t off = row * 128 + ((c16 ^ (row & 7)) << 4);
+              bf16 *gdst = a.gates + ((size_t)t * M + m) * 4 * C + ch0 + c16 * 8;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(gdst + (size_t)g * C) = *reinterpret_cast<const uint4 *>(stG + g * 4096 + off);
+              const size_t o = ((size_t)t * M + m) * C + ch0 + c16 * 8;
+              *reinterpret_cast<uint4 *>(a.c_all + o) = *reinterpret_cast<const uint4 *>(stC + off);
+              *reinterpret_cast<uint4 *>(a.h_all + o) = *reinterpret_cast<const uint4 *>(stH + off);
+            }
+          }
+          // publish: h_t (this pass's channels) is in global memory; make it visible to TMA reads and count the warp in
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && t + 1 < a.L) {
+            unsigned *f = a.flags + (size_t)tile * a.L + t;
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// 3D bf16 tensor map [d0 (contiguous), d1, d2] with element pitches ld1, ld2; box [b0, b1, 1], 128B swizzle
+int make_map3(CUtensorMap *out, const void *ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1, uint64_t ld2, uint32_t b0,
+              uint32_t b1) {
+  auto fn = get_encode_fn();
+  LEOD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (driver too old?)");
+  LEOD_REQUIRE(((uintptr_t)ptr & 15) == 0 && (ld1 * 2) % 16 == 0 && (ld2 * 2) % 16 == 0, "TMA operand %p / pitches not 16-byte aligned", ptr);
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {ld1 * 2, ld2 * 2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LEOD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with %d", (int)r);
+  return 0;
+}
 }  // namespace
 
 static int num_sms() {
@@ -803,6 +1112,43 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   } else {
     gemm_nt_tc_kernel<EPI_NONE><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
   }
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+
+// Whole-window ConvLSTM recurrence of one stage (see lstm_seq_fwd_kernel).  gates: [L][M][4C] holding the x-half
+// pre-activations (+bias) on entry, the activated gates on exit.  Wh: prepared [4C][ldw] weight, columns 0..C-1 = hidden half.
+int lstm_seq_fwd_tc(void *gates, const void *Wh, int ldw, const void *h0, const void *c0, void *h_all, void *c_all, unsigned *flags, int M,
+                    int C, int L, cudaStream_t st) {
+  LEOD_REQUIRE(C % 16 == 0 && M > 0 && L > 0, "lstm_seq_fwd_tc: bad shape M=%d C=%d L=%d", M, C, L);
+  LstmSeqArgs a;
+  a.gates = (bf16 *)gates; a.c0 = (const bf16 *)c0; a.h_all = (bf16 *)h_all; a.c_all = (bf16 *)c_all; a.flags = flags;
+  a.M = M; a.C = C; a.L = L;
+  a.CW = 0;
+  for (int cw = 64; cw >= 16; cw -= 16)
+    if (C % cw == 0) { a.CW = cw; break; }
+  a.npass = C / a.CW;
+  a.tiles_m = ceil_div(M, TILE_M);
+  a.split = (a.npass > 1 && a.tiles_m * a.npass <= num_sms()) ? 1 : 0;
+  a.has_h0 = h0 != nullptr;
+  a.nkb = ceil_div(C, TILE_K);
+  const int stage_bytes = A_STAGE_BYTES + 4 * a.CW * TILE_K * 2;
+  a.stages = std::max(2, std::min(4, (int)((224 * 1024 - 4 * LS_WARP_STAGE - 2048) / stage_bytes)));
+  CUtensorMap mH, mH0, mW;
+  LEOD_TRY(make_map3(&mH, h_all, C, M, L, C, (uint64_t)M * C, TILE_K, TILE_M));
+  LEOD_TRY(make_map3(&mH0, h0 ? h0 : h_all, C, M, 1, C, (uint64_t)M * C, TILE_K, TILE_M));
+  LEOD_TRY(make_map(&mW, Wh, C, 4 * C, ldw, TILE_K, a.CW));
+  const size_t smem = (size_t)a.stages * stage_bytes + 4 * LS_WARP_STAGE + 1024 + (2 * a.stages + 4) * 8 + 64;
+  LEOD_REQUIRE(smem <= 227 * 1024, "lstm_seq_fwd_tc: shared memory %zu", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LEOD_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    attr_set = true;
+  }
+  LEOD_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (size_t)a.tiles_m * L, st));
+  const int grid = a.split ? a.tiles_m * a.npass : std::min(a.tiles_m, num_sms());
+  lstm_seq_fwd_kernel<<<grid, LS_THREADS, smem, st>>>(mH, mH0, mW, a);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
