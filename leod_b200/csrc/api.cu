@@ -23,6 +23,8 @@ bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 }  // namespace
 
+bool leod_profiling_on() { return g_prof_on; }
+
 ProfScope::ProfScope(int kind, double flops, double bytes, cudaStream_t st_, int d0, int d1, int d2) : slot(-1), st(st_) {
   if (!g_prof_on) return;
   ProfRec r;

@@ -79,6 +79,8 @@ struct leod_backbone {
   void *seq_col0 = nullptr;      // stem patch matrix of the whole window [L*B*Ho*Wo, Kp] (kept from forward to backward)
   int64_t seq_col0_imgs = 0;
   bool col0_live = false;
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned *seq_flags = nullptr;  // per-(tile, timestep) arrival counters of the fused recurrence kernels
   int fused_lstm = 1;        // set for the duration of a sequence-mode forward/backward pair
   size_t esz() const { return cfg.dtype == LEOD_BF16 ? 2 : 4; }
@@ -86,6 +88,16 @@ struct leod_backbone {
 };
 
 namespace {
+
+int ensure_side_streams(leod_backbone *h) {
+  if (h->ev_fork) return 0;
+  for (int i = 0; i < 4; ++i) {
+    LEOD_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+    LEOD_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+  }
+  LEOD_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  return 0;
+}
 
 int64_t add_param(leod_backbone *h, const std::string &name, std::initializer_list<int64_t> shape) {
   ParamEntry e;
@@ -395,7 +407,7 @@ int front_bwd(leod_backbone *h, int s, int64_t nimg, const SB &b, const GB &g, v
 // weight gradients of one stage over `nimg` images worth of rows (all timesteps at once in sequence mode).
 // The LSTM's hidden-state half is paired by the caller (it needs h_{t-1}).
 int stage_wgrads(leod_backbone *h, int s, int64_t nimg, const void *in, int x_dtype, int x_h, int x_w, const SB &b, const GB &g,
-                 cudaStream_t st) {
+                 cudaStream_t st, int parts = 3 /* bit 0: linear layers, bit 1: downsample conv (uses the shared patch workspace) */) {
   const StageD &d = h->d[s];
   const StageP &p = h->p[s];
   const StageW &w = h->w[s];
@@ -403,15 +415,18 @@ int stage_wgrads(leod_backbone *h, int s, int64_t nimg, const void *in, int x_dt
   float *G = h->grads;
   const int64_t rows_per_img = (int64_t)d.Ho * d.Wo, e = (int64_t)h->esz();
   const int M = (int)(nimg * rows_per_img);
-  LEOD_TRY(gemm_tn(h, g.dgates, 4 * C, b.x2[1], C, G + p.lstmw, 2 * C, G + p.lstmb, M, 4 * C, C, st));
-  for (int k = 0; k < 2; ++k) {
-    const BlockP &q = p.blk[k];
-    const BlockW &bw = w.blk[k];
-    LEOD_TRY(gemm_tn(h, g.dy2[k], C, b.a[k], R * C, bw.G2, R * C, bw.s2, M, C, R * C, st));
-    LEOD_TRY(gemm_tn(h, g.du[k], R * C, b.xn2[k], C, G + q.fc1w, C, G + q.fc1b, M, R * C, C, st));
-    LEOD_TRY(gemm_tn(h, g.dy1[k], C, b.att[k], C, bw.Gproj, C, bw.sproj, M, C, C, st));
-    LEOD_TRY(gemm_tn(h, g.dqkv[k], 3 * C, k == 1 ? b.xn1 : b.x0, C, G + q.qkvw, C, G + q.qkvb, M, 3 * C, C, st));
+  if (parts & 1) {
+    LEOD_TRY(gemm_tn(h, g.dgates, 4 * C, b.x2[1], C, G + p.lstmw, 2 * C, G + p.lstmb, M, 4 * C, C, st));
+    for (int k = 0; k < 2; ++k) {
+      const BlockP &q = p.blk[k];
+      const BlockW &bw = w.blk[k];
+      LEOD_TRY(gemm_tn(h, g.dy2[k], C, b.a[k], R * C, bw.G2, R * C, bw.s2, M, C, R * C, st));
+      LEOD_TRY(gemm_tn(h, g.du[k], R * C, b.xn2[k], C, G + q.fc1w, C, G + q.fc1b, M, R * C, C, st));
+      LEOD_TRY(gemm_tn(h, g.dy1[k], C, b.att[k], C, bw.Gproj, C, bw.sproj, M, C, C, st));
+      LEOD_TRY(gemm_tn(h, g.dqkv[k], 3 * C, k == 1 ? b.xn1 : b.x0, C, G + q.qkvw, C, G + q.qkvb, M, 3 * C, C, st));
+    }
   }
+  if (!(parts & 2)) return 0;
   const bool keep = s == 0 && h->col0_live && h->seq_col0 && nimg == h->seq_col0_imgs;   // patches still there from the forward pass
   const int64_t chunk_imgs = keep ? nimg : std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
   for (int64_t i0 = 0; i0 < nimg; i0 += chunk_imgs) {
@@ -553,6 +568,11 @@ extern "C" void leod_backbone_destroy(leod_backbone_t *h) {
   if (h->seq_arena) cudaFree(h->seq_arena);
   if (h->seq_col0) cudaFree(h->seq_col0);
   if (h->seq_flags) cudaFree(h->seq_flags);
+  for (int i = 0; i < 4; ++i) {
+    if (h->side[i]) cudaStreamDestroy(h->side[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   delete h;
 }
 
@@ -812,17 +832,34 @@ extern "C" int leod_backbone_seq_bwd(leod_backbone_t *h, const void *x, int x_dt
     LEOD_TRY(gemm_nt(h, mk(g.dgates, (int)(4 * C), w.WlT, (int)(4 * C), g.dy2[1], (int)C, (int)(M * L), (int)C, (int)(4 * C)), st));
     LEOD_TRY(front_bwd(h, s, (int64_t)B * L, b, g, s > 0 ? h->ws_hint : nullptr, st));
   }
-  // weight gradients: one GEMM per layer over all L timesteps
+  // weight gradients: one GEMM per layer over all L timesteps.  The ~50 GEMMs are independent of each other and many
+  // are too small to fill 148 SMs, so the linear layers of every stage run on their own side stream; the downsample
+  // convolutions share the patch workspace and stay in order on the caller's stream.  (Serial when the per-launch
+  // profiler is on: its events assume one stream.)
+  const bool fork = !leod_profiling_on();
+  if (fork) LEOD_TRY(ensure_side_streams(h));
+  if (fork) {
+    LEOD_CUDA(cudaEventRecord(h->ev_fork, st));
+    for (int s = 0; s < 4; ++s) LEOD_CUDA(cudaStreamWaitEvent(h->side[s], h->ev_fork, 0));
+  }
   for (int s = 0; s < 4; ++s) {
     const StageD &d = h->d[s];
     const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
     const SB b = sb_at(h, h->seq_arena, lay[s], s, B, 0);
     const GB g = gb_at(h, h->seq_arena, lay[s], s, B, 0);
-    LEOD_TRY(stage_wgrads(h, s, (int64_t)B * L, s == 0 ? x : h_all[s - 1], x_dtype, x_h, x_w, b, g, st));
+    cudaStream_t ss = fork ? h->side[s] : st;
+    LEOD_TRY(stage_wgrads(h, s, (int64_t)B * L, s == 0 ? x : h_all[s - 1], x_dtype, x_h, x_w, b, g, ss, 1));
     float *dWl_h = h->grads + h->p[s].lstmw + C;
     if (L > 1)   // dgates of timesteps 1..L-1 pair with the hidden states of timesteps 0..L-2
-      LEOD_TRY(gemm_tn(h, (char *)g.dgates + M * 4 * C * e, 4 * C, h_all[s], C, dWl_h, 2 * C, nullptr, (int)((L - 1) * M), 4 * C, C, st));
-    if (h0 && h0[s]) LEOD_TRY(gemm_tn(h, g.dgates, 4 * C, h0[s], C, dWl_h, 2 * C, nullptr, (int)M, 4 * C, C, st));
+      LEOD_TRY(gemm_tn(h, (char *)g.dgates + M * 4 * C * e, 4 * C, h_all[s], C, dWl_h, 2 * C, nullptr, (int)((L - 1) * M), 4 * C, C, ss));
+    if (h0 && h0[s]) LEOD_TRY(gemm_tn(h, g.dgates, 4 * C, h0[s], C, dWl_h, 2 * C, nullptr, (int)M, 4 * C, C, ss));
+    LEOD_TRY(stage_wgrads(h, s, (int64_t)B * L, s == 0 ? x : h_all[s - 1], x_dtype, x_h, x_w, b, g, st, 2));
+  }
+  if (fork) {
+    for (int s = 0; s < 4; ++s) {
+      LEOD_CUDA(cudaEventRecord(h->ev_join[s], h->side[s]));
+      LEOD_CUDA(cudaStreamWaitEvent(st, h->ev_join[s], 0));
+    }
   }
   h->col0_live = false;
   return 0;

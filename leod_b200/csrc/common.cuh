@@ -44,6 +44,8 @@ struct ProfScope {
   ~ProfScope();
 };
 
+bool leod_profiling_on();
+
 #define LEOD_TRY(expr)        \
   do {                        \
     int r__ = (expr);         \

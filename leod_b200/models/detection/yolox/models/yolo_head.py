@@ -79,27 +79,43 @@ class YOLOXHead(nn.Module):
 
     def forward(self, xin, labels=None, pred_probs=None):
         assert pred_probs is None
-        def level(k, x):
+        capturing = xin[0].is_cuda and torch.cuda.is_current_stream_capturing() and not self._has_sync_bn()
+
+        def level(k, x, side=None):
             x = self.stems[k](x)
-            cls_feat = self.cls_convs[k](x)
-            reg_feat = self.reg_convs[k](x)
+            if side is None:
+                cls_feat = self.cls_convs[k](x)
+                reg_feat = self.reg_convs[k](x)
+            else:       # the classification and regression towers of a level are independent too
+                here = torch.cuda.current_stream()
+                side.wait_stream(here)
+                with torch.cuda.stream(side):
+                    cls_feat = self.cls_convs[k](x)
+                    cls_out = self.cls_preds[k](cls_feat)
+                    cls_out.record_stream(here)
+                reg_feat = self.reg_convs[k](x)
+                reg_out, obj_out = self.reg_preds[k](reg_feat), self.obj_preds[k](reg_feat)
+                here.wait_stream(side)
+                return torch.cat((reg_out, obj_out, cls_out), 1)
             return torch.cat((self.reg_preds[k](reg_feat), self.obj_preds[k](reg_feat), self.cls_preds[k](cls_feat)), 1)
 
-        if xin[0].is_cuda and torch.cuda.is_current_stream_capturing() and not self._has_sync_bn():
-            # CUDA-graph capture (detector.py, _GraphedDetect): the three pyramid levels are independent chains of small
-            # kernels; fork them onto side streams so the captured graph (forward and backward) runs them side by side
+        if capturing:
+            # CUDA-graph capture (detector.py, _GraphedDetect): the three pyramid levels (and the two towers of each) are
+            # independent chains of small kernels; fork them onto side streams so the captured graph (forward and
+            # backward) runs them side by side
             cur = torch.cuda.current_stream()
+            n = len(xin)
             if not hasattr(self, '_side_streams'):
-                self._side_streams = [torch.cuda.Stream() for _ in range(len(xin) - 1)]
-            raw = [None] * len(xin)
-            for k in range(1, len(xin)):
+                self._side_streams = [torch.cuda.Stream() for _ in range(2 * n - 1)]
+            raw = [None] * n
+            for k in range(1, n):
                 st = self._side_streams[k - 1]
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
-                    raw[k] = level(k, xin[k])
+                    raw[k] = level(k, xin[k], side=self._side_streams[n - 1 + k])
                     raw[k].record_stream(cur)
-            raw[0] = level(0, xin[0])
-            for st in self._side_streams:
+            raw[0] = level(0, xin[0], side=self._side_streams[n - 1])
+            for st in self._side_streams[:n - 1]:
                 cur.wait_stream(st)
         else:
             raw = [level(k, x) for k, x in enumerate(xin)]
