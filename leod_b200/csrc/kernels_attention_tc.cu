@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16))
 // Backward: recompute P, dP = dO V^T, dS = P o (dP - rowsum(P o dP)) * scale; dQ = dS K from registers; P and dS go
 // to shared memory once and dK = dS^T Q, dV = P^T dO read them (and Q, dO) through transposing ldmatrix loads.
 template <int NT_S, int NT_O, int KS>
-__global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16), 3)
+__global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16), 4)
     attn_bwd_tc_kernel(const bf16 *__restrict__ qkv, const bf16 *__restrict__ dout, bf16 *__restrict__ dqkv, int H, int W, int C,
                        int ph, int pw, int window, float scale) {
   constexpr int TP = ((NT_S * 8 + 15) / 16) * 16;

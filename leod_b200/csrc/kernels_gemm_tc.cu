@@ -877,9 +877,19 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const __gri
   } else {
     const int quarter = warp & 3;
     uint8_t *stG = stage_base + (warp - 2) * LS_WARP_STAGE, *stC = stG + 4 * 4096, *stH = stC + 4096;
-    const int ppr = a.CW >> 3;                    // 16-byte pieces per row segment (6 or 8)
-    const int pieces = 32 * ppr;
+    const int ppr = a.CW >> 3;                    // 16-byte pieces per row segment (2..8); a lane moves ppr pieces per tensor
     const int nchunk = a.CW >> 4;                 // 16-channel chunks per pass
+    const uint32_t stG_u32 = smem_u32(stG), stC_u32 = smem_u32(stC);
+    int prow[8], pcol[8];
+    uint32_t poff[8];                             // piece k of this lane: tile row, channel offset, swizzled staging offset
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int q = lane + 32 * k;
+      prow[k] = q / ppr;
+      const int c16 = q - prow[k] * ppr;
+      pcol[k] = c16 * 8;
+      poff[k] = prow[k] * 128 + ((c16 ^ (prow[k] & 7)) << 4);
+    }
     int j = 0;
     for (int t = 0; t < a.L; ++t) {
       const bool mma = !(t == 0 && !a.has_h0);
@@ -889,17 +899,21 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const __gri
           const int pass = pass_first + p;
           const int ch0 = pass * a.CW;
           // ---- stage Gx (4 gates) and c_{t-1}: coalesced 16-byte async copies into the swizzled tiles
-          for (int q = lane; q < pieces; q += 32) {
-            const int row = q / ppr, c16 = q - row * ppr;
-            const int m = m_base + row;
-            const bool ok = m < M;
-            const uint32_t off = row * 128 + ((c16 ^ (row & 7)) << 4);
-            const bf16 *gsrc = a.gates + ((size_t)t * M + (ok ? m : 0)) * 4 * C + ch0 + c16 * 8;
+          {
+            const bf16 *gbase = a.gates + (size_t)t * M * 4 * C + ch0;
+            const bf16 *cbase = t > 0 ? a.c_all + (size_t)(t - 1) * M * C + ch0 : (a.c0 ? a.c0 + ch0 : nullptr);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) cp_async16(smem_u32(stG + g * 4096 + off), gsrc + (size_t)g * C, ok);
-            const bf16 *cprev = t > 0 ? a.c_all + ((size_t)(t - 1) * M + (ok ? m : 0)) * C + ch0 + c16 * 8
-                                      : (a.c0 ? a.c0 + (size_t)(ok ? m : 0) * C + ch0 + c16 * 8 : nullptr);
-            cp_async16(smem_u32(stC + off), cprev ? (const void *)cprev : (const void *)a.gates, ok && cprev != nullptr);
+            for (int k = 0; k < 8; ++k) {
+              if (k < ppr) {
+                const int m = m_base + prow[k];
+                const bool ok = m < M;
+                const size_t mo = ok ? (size_t)m : 0;
+                const bf16 *gsrc = gbase + mo * 4 * C + pcol[k];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) cp_async16(stG_u32 + g * 4096 + poff[k], gsrc + (size_t)g * C, ok);
+                cp_async16(stC_u32 + poff[k], cbase ? (const void *)(cbase + mo * C + pcol[k]) : (const void *)a.gates, ok && cbase != nullptr);
+              }
+            }
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
           int buf = 0;
@@ -992,21 +1006,25 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const __gri
             __syncwarp();
           }
           // ---- write activated gates, c_t, h_t as 16-byte pieces of contiguous row segments
-          for (int q = lane; q < pieces; q += 32) {
-            const int row = q / ppr, c16 = q - row * ppr;
-            const int m = m_base + row;
-            if (m < M) {
-              const uint32_t off = row * 128 + ((c16 ^ (row & 7)) << 4);
-              bf16 *gdst = a.gates + ((size_t)t * M + m) * 4 * C + ch0 + c16 * 8;
+          {
+            bf16 *gbase = a.gates + (size_t)t * M * 4 * C + ch0;
+            bf16 *cdst = a.c_all + (size_t)t * M * C + ch0, *hdst = a.h_all + (size_t)t * M * C + ch0;
 #pragma unroll
-              for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(gdst + (size_t)g * C) = *reinterpret_cast<const uint4 *>(stG + g * 4096 + off);
-              const size_t o = ((size_t)t * M + m) * C + ch0 + c16 * 8;
-              *reinterpret_cast<uint4 *>(a.c_all + o) = *reinterpret_cast<const uint4 *>(stC + off);
-              *reinterpret_cast<uint4 *>(a.h_all + o) = *reinterpret_cast<const uint4 *>(stH + off);
+            for (int k = 0; k < 8; ++k) {
+              if (k < ppr) {
+                const int m = m_base + prow[k];
+                if (m < M) {
+                  bf16 *gdst = gbase + (size_t)m * 4 * C + pcol[k];
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(gdst + (size_t)g * C) = *reinterpret_cast<const uint4 *>(stG + g * 4096 + poff[k]);
+                  *reinterpret_cast<uint4 *>(cdst + (size_t)m * C + pcol[k]) = *reinterpret_cast<const uint4 *>(stC + poff[k]);
+                  *reinterpret_cast<uint4 *>(hdst + (size_t)m * C + pcol[k]) = *reinterpret_cast<const uint4 *>(stH + poff[k]);
+                }
+              }
             }
           }
           // publish: h_t (this pass's channels) is in global memory; make it visible to TMA reads and count the warp in
-          __threadfence();
+          // (generic-proxy stores -> proxy fence -> warp barrier -> one cumulative release per warp)
           asm volatile("fence.proxy.async;" ::: "memory");
           __syncwarp();
           if (lane == 0 && t + 1 < a.L) {

@@ -323,3 +323,54 @@ def test_full_size_matches_oracle(size, dataset, B):
         for s in (1, 2, 3, 4):
             assert rel_err(feats[s].float().cpu(), ref[0][s]) < (1e-3 if dtype == 'fp32' else 2.5e-2), (dtype, s)
         assert rel_err(preds.cpu(), ref[1]) < (1e-3 if dtype == 'fp32' else 2.5e-2)
+        # the whole-window path (stage-major schedule, fused ConvLSTM recurrence kernel for bf16) against the same oracle
+        with torch.inference_mode():
+            feats_seq, states_seq = m.backbone.forward_sequence(x.cuda(), None)
+        for s in (1, 2, 3, 4):
+            assert rel_err(feats_seq[s][-1].float().cpu(), ref[0][s]) < (1e-3 if dtype == 'fp32' else 2.5e-2), ('seq', dtype, s)
+            assert rel_err(states_seq[s - 1][1].float(), states[s - 1][1].float()) < (1e-4 if dtype == 'fp32' else 3e-2), ('seq c', dtype, s)
+
+
+@pytest.mark.parametrize('size,dataset,B,L', [('base', 'gen4', 1, 3), ('tiny', 'gen1', 2, 4)])
+def test_full_size_sequence_backward_equals_per_step(size, dataset, B, L):
+    """Full-size bf16 training windows: forward_sequence + backward (batched stages, fused recurrence, deferred and
+    multi-stream weight gradients) against the per-timestep calls — parameter gradients of the whole backbone."""
+    from leod_b200.config import DATASETS, make_model_cfg
+    from leod_b200.models.detection.yolox_extension.models.detector import YoloXDetector
+    torch.manual_seed(1)
+    fh, fw = DATASETS[dataset]['frame_hw']
+    x = ((torch.rand(L, B, 20, fh, fw) < 0.1).float() * torch.randint(1, 6, (L, B, 20, fh, fw))).to(torch.uint8).cuda()
+    m = YoloXDetector(make_model_cfg(size=size, dataset=dataset, compute_dtype='bf16'))
+    with torch.no_grad():
+        for k, p in m.named_parameters():
+            if k.endswith('gamma'):
+                p.fill_(0.5)
+    m.cuda().train()
+    bb = m.backbone
+    gen = torch.Generator(device='cuda').manual_seed(2)
+    R, grads = None, []
+    for mode in ('step', 'seq'):
+        m.zero_grad(set_to_none=True)
+        if mode == 'step':
+            states, hs = None, {k: [] for k in (1, 2, 3, 4)}
+            for t in range(L):
+                f, states = bb(x[t], states)
+                for k in hs:
+                    hs[k].append(f[k])
+            feats = {k: torch.stack(v) for k, v in hs.items()}
+        else:
+            feats, states = bb.forward_sequence(x, None)
+        if R is None:
+            R = {k: torch.randn(v.shape, device='cuda', generator=gen) for k, v in feats.items()}
+        loss = sum((feats[k].float() * R[k]).mean() for k in feats)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads.append(bb.flat_grads.clone())
+    assert rel_err(grads[1], grads[0]) < 5e-2
+    # per-tensor check so a wrong small tensor cannot hide behind a large one
+    for name, off, shape in bb._layout['entries']:
+        n = 1
+        for d_ in shape:
+            n *= d_
+        a, b = grads[0][off:off + n], grads[1][off:off + n]
+        assert float((a - b).abs().max()) <= 8e-2 * float(a.abs().max()) + 1e-6, name
