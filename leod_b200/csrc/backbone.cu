@@ -362,7 +362,8 @@ int lstm_bwd(leod_backbone *h, int s, int M, const void *gates, const void *c_pr
 
 // input gradients of the two blocks and the downsample; output-gradient tensors land in g for the deferred
 // weight-gradient GEMMs.  hint_out (stage > 0): gradient w.r.t. the stage input (previous stage's h), channels-last.
-int front_bwd(leod_backbone *h, int s, int64_t nimg, const SB &b, const GB &g, void *hint_out, cudaStream_t st) {
+int front_bwd(leod_backbone *h, int s, int64_t nimg, const SB &b, const GB &g, void *hint_out, cudaStream_t st,
+              const void *hint_res = nullptr /* added to the hint: the caller's own gradient w.r.t. the previous stage's h */) {
   const StageD &d = h->d[s];
   const StageP &p = h->p[s];
   const StageW &w = h->w[s];
@@ -397,8 +398,8 @@ int front_bwd(leod_backbone *h, int s, int64_t nimg, const SB &b, const GB &g, v
     for (int64_t i0 = 0; i0 < nimg; i0 += chunk_imgs) {
       const int n = (int)std::min<int64_t>(chunk_imgs, nimg - i0);
       LEOD_TRY(gemm_nt(h, mk((char *)g.dy0 + i0 * rows_per_img * C * e, C, w.WconvT, C, h->ws_col, d.Kp, (int)(n * rows_per_img), d.K, C), st));
-      LEOD_TRY(col2im_nhwc(dt, h->ws_col, d.Kp, nullptr, (char *)hint_out + i0 * d.Hi * d.Wi * d.Cin * e, n, d.Hi, d.Wi, d.Cin, d.ksz,
-                           d.stride, d.pad, st));
+      LEOD_TRY(col2im_nhwc(dt, h->ws_col, d.Kp, hint_res ? (const char *)hint_res + i0 * d.Hi * d.Wi * d.Cin * e : nullptr,
+                           (char *)hint_out + i0 * d.Hi * d.Wi * d.Cin * e, n, d.Hi, d.Wi, d.Cin, d.ksz, d.stride, d.pad, st));
     }
   }
   return 0;
@@ -812,25 +813,38 @@ extern "C" int leod_backbone_seq_bwd(leod_backbone_t *h, const void *x, int x_dt
     const SB b = sb_at(h, h->seq_arena, lay[s], s, B, 0);
     const GB g = gb_at(h, h->seq_arena, lay[s], s, B, 0);
     const char *cs = (const char *)h->seq_arena + lay[s].c_all * e;
-    const bool have_hint = s < 3;   // ws_hint = d loss / d h_all[s] from stage s+1's downsample, all timesteps
-    for (int t = L - 1; t >= 0; --t) {
-      const void *cp = t == 0 ? (c0 ? c0[s] : nullptr) : cs + (t - 1) * M * C * e;
-      const void *dh_head = (dh_all && dh_all[s]) ? (const char *)dh_all[s] + t * M * C * e : nullptr;
-      const void *dh_hint = have_hint ? (const char *)h->ws_hint + t * M * C * e : nullptr;
-      const void *dh_next = t < L - 1 ? h->ws_dhc[s] : nullptr;            // from timestep t+1
-      const void *dc_in = t < L - 1 ? h->ws_dcc[s] : (dc_last ? dc_last[s] : nullptr);
-      const bool has_hp = t > 0 || (h0 && h0[s]);
-      void *dc_out_ptr = (t == 0 && dc0 && dc0[s]) ? dc0[s] : h->ws_dcc[s];
-      void *dh_out_ptr = !has_hp ? nullptr : ((t == 0) ? ((dh0 && dh0[s]) ? dh0[s] : nullptr) : h->ws_dhc[s]);
-      void *dgt = (char *)g.dgates + t * M * 4 * C * e;
-      LEOD_TRY(lstm_pointwise_bwd(h->cfg.dtype, (const char *)b.gates + t * M * 4 * C * e, cp, cs + t * M * C * e, dh_head, dh_hint, dc_in,
-                                  dgt, dc_out_ptr, (int)M, (int)C, st, dh_next));
-      if (dh_out_ptr)
-        LEOD_TRY(gemm_nt(h, mk(dgt, (int)(4 * C), eoff(h, w.WlT, C * 4 * C), (int)(4 * C), dh_out_ptr, (int)C, (int)M, (int)C, (int)(4 * C)), st));
+    // external gradient w.r.t. h_all[s], all timesteps: the caller's (head) gradient, plus - for s < 3 - the gradient
+    // through stage s+1's downsample, which front_bwd(s+1) has already added into ws_hint
+    const char *dh_ext = s < 3 ? (const char *)h->ws_hint : ((dh_all && dh_all[s]) ? (const char *)dh_all[s] : nullptr);
+    // The fused backward recurrence re-streams a 128 x 4C operand tile per step and CTA: it wins while there are enough
+    // token tiles to fill the GPU (measured: stages 1-2 of RVT-S at B=8); small late stages keep per-step launches, whose
+    // GEMMs spread one timestep over ~120 CTAs.
+    if (h->cfg.dtype == LEOD_BF16 && h->gemm_impl == 1 && h->fused_lstm && C % 16 == 0 && M >= 40 * 128) {
+      ProfScope ps(PK_LSTM, 2.0 * M * L * 4 * C * C + 30.0 * M * L * C, 13.0 * M * L * C * e, st, (int)M, (int)C, -L);
+      const bool want_dh0 = h0 && h0[s] && dh0 && dh0[s];
+      LEOD_TRY(lstm_seq_bwd_tc(b.gates, cs, c0 ? c0[s] : nullptr, dh_ext, dc_last ? dc_last[s] : nullptr, g.dgates, h->ws_dcc[s],
+                               (dc0 && dc0[s]) ? dc0[s] : nullptr, want_dh0 ? dh0[s] : nullptr, eoff(h, w.WlT, C * 4 * C), (int)(4 * C),
+                               h->seq_flags, (int)M, (int)C, L, st));
+    } else {
+      for (int t = L - 1; t >= 0; --t) {
+        const void *cp = t == 0 ? (c0 ? c0[s] : nullptr) : cs + (t - 1) * M * C * e;
+        const void *dh_e = dh_ext ? dh_ext + t * M * C * e : nullptr;
+        const void *dh_next = t < L - 1 ? h->ws_dhc[s] : nullptr;            // from timestep t+1
+        const void *dc_in = t < L - 1 ? h->ws_dcc[s] : (dc_last ? dc_last[s] : nullptr);
+        const bool has_hp = t > 0 || (h0 && h0[s]);
+        void *dc_out_ptr = (t == 0 && dc0 && dc0[s]) ? dc0[s] : h->ws_dcc[s];
+        void *dh_out_ptr = !has_hp ? nullptr : ((t == 0) ? ((dh0 && dh0[s]) ? dh0[s] : nullptr) : h->ws_dhc[s]);
+        void *dgt = (char *)g.dgates + t * M * 4 * C * e;
+        LEOD_TRY(lstm_pointwise_bwd(h->cfg.dtype, (const char *)b.gates + t * M * 4 * C * e, cp, cs + t * M * C * e, dh_e, nullptr, dc_in,
+                                    dgt, dc_out_ptr, (int)M, (int)C, st, dh_next));
+        if (dh_out_ptr)
+          LEOD_TRY(gemm_nt(h, mk(dgt, (int)(4 * C), eoff(h, w.WlT, C * 4 * C), (int)(4 * C), dh_out_ptr, (int)C, (int)M, (int)C, (int)(4 * C)), st));
+      }
     }
     // d loss / d x2 for all timesteps, then the two blocks and the downsample
     LEOD_TRY(gemm_nt(h, mk(g.dgates, (int)(4 * C), w.WlT, (int)(4 * C), g.dy2[1], (int)C, (int)(M * L), (int)C, (int)(4 * C)), st));
-    LEOD_TRY(front_bwd(h, s, (int64_t)B * L, b, g, s > 0 ? h->ws_hint : nullptr, st));
+    LEOD_TRY(front_bwd(h, s, (int64_t)B * L, b, g, s > 0 ? h->ws_hint : nullptr, st,
+                       (s > 0 && dh_all && dh_all[s - 1]) ? dh_all[s - 1] : nullptr));
   }
   // weight gradients: one GEMM per layer over all L timesteps.  The ~50 GEMMs are independent of each other and many
   // are too small to fill 148 SMs, so the linear layers of every stage run on their own side stream; the downsample

@@ -108,6 +108,8 @@ int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int l
                cudaStream_t st);
 int lstm_seq_fwd_tc(void *gates, const void *Wh, int ldw, const void *h0, const void *c0, void *h_all, void *c_all, unsigned *flags,
                     int M, int C, int L, cudaStream_t st);
+int lstm_seq_bwd_tc(const void *gates, const void *c_all, const void *c0, const void *dh, const void *dc_last, void *dgates, void *dc_ws,
+                    void *dc0, void *dh0, const void *WhT, int ldw, unsigned *flags, int M, int C, int L, cudaStream_t st);
 // kernels_attention.cu
 int attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, int C, int dh, int ph, int pw, int window,
                   cudaStream_t st);

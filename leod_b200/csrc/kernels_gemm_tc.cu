@@ -752,6 +752,7 @@ struct LstmSeqArgs {
 constexpr int LS_THREADS = 192;
 constexpr int LS_WARP_STAGE = 4 * 4096 + 4096 + 4096;   // per gate-math warp: gates [4][32 rows][128 B], c, h
 
+__device__ __forceinline__ int64_t round_up_dev(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
@@ -1043,6 +1044,289 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const __gri
   }
 }
 
+// ---- backward of the recurrence, same skeleton run backwards in time:
+//   dh_t = dh_ext_t + dgates_{t+1} W_h ;  dc = dc_{t+1} + dh_t o (1 - tanh(c_t)^2) ;  dgates_t = (dc c_{t-1} f(1-f), dc g i(1-i),
+//   dh_t tanh(c_t) o(1-o), dc i (1-g^2)) ;  dc_t-1 = dc f.        (models/layers/rnn.py:57-68 differentiated)
+// dgates_t goes to global memory (the weight-gradient and input-gradient GEMMs need it anyway) and is the A operand
+// (K = 4C) of the next step through TMA; one extra GEMM-only iteration produces the gradient w.r.t. h0.
+struct LstmBwdArgs {
+  const bf16 *gates, *c_all, *c0, *dh, *dc_last;
+  bf16 *dgates, *dc_ws, *dc0, *dh0;
+  unsigned *flags;
+  int M, C, L, CWb, npass, split, nkb, stages, tiles_m;
+};
+constexpr int LB_WARP_STAGE = 8 * 4096;   // per gate-math warp: gates [4], c_prev, c, dh, dc tiles of [32 rows][128 B]
+
+__global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap mapG,   // dgates [4C, M, L]
+                                                                      const __grid_constant__ CUtensorMap mapW,   // W_h^T [4C, C]
+                                                                      const LstmBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_stage_bytes = a.CWb * TILE_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + (int)round_up_dev(b_stage_bytes, 1024);
+  uint8_t *stage_base = smem + (size_t)a.stages * stage_bytes;
+  uint64_t *bars = (uint64_t *)(stage_base + 4 * LB_WARP_STAGE);
+  uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages, *tmem_empty = tmem_full + 2;
+  uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = a.C, M = a.M, L = a.L;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tmem_full[b]), 1);
+      mbar_init(smem_u32(&tmem_empty[b]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tile_first = a.split ? (int)blockIdx.x / a.npass : (int)blockIdx.x;
+  const int tile_step = a.split ? a.tiles_m : (int)gridDim.x;
+  const int pass_first = a.split ? (int)blockIdx.x % a.npass : 0;
+  const int pass_count = a.split ? 1 : a.npass;
+  const unsigned flag_target = 4u * (unsigned)a.npass;
+  const int t_last = a.dh0 ? -1 : 0;    // t = -1: GEMM-only iteration for the gradient w.r.t. h0
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = L - 2; t >= t_last; --t) {
+        for (int tile = tile_first; tile < a.tiles_m; tile += tile_step) {
+          {   // dgates_{t+1} of this tile: all channel passes written and visible to the async proxy
+            const unsigned *f = a.flags + (size_t)tile * L + (t + 1);
+            unsigned v;
+            const long long t0 = clock64();
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+              if (v < flag_target && clock64() - t0 > 20000000000LL) __trap();
+            } while (v < flag_target);
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          for (int p = 0; p < pass_count; ++p) {
+            const int pass = pass_first + p;
+            for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+              const int s = it % a.stages;
+              const uint32_t ph = (it / a.stages) & 1;
+              mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+              const uint32_t fb = smem_u32(&full_bar[s]);
+              mbar_expect_tx(fb, A_STAGE_BYTES + b_stage_bytes);
+              const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
+              tma_load_3d(sa, &mapG, fb, kb * TILE_K, tile * TILE_M, t + 1);
+              tma_load_2d(sb, &mapW, fb, kb * TILE_K, pass * a.CWb);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TILE_M, a.CWb, 0, 0);
+      int it = 0, j = 0;
+      for (int t = L - 2; t >= t_last; --t) {
+        for (int tile = tile_first; tile < a.tiles_m; tile += tile_step) {
+          for (int p = 0; p < pass_count; ++p, ++j) {
+            const int buf = j & 1;
+            mbar_wait(smem_u32(&tmem_empty[buf]), ((j >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)(buf * 256);
+            for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+              const int s = it % a.stages;
+              const uint32_t ph = (it / a.stages) & 1;
+              mbar_wait(smem_u32(&full_bar[s]), ph);
+              tc_fence_after();
+              const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
+              const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
+#pragma unroll
+              for (int k = 0; k < TILE_K / 16; ++k) tc_mma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              tc_commit(smem_u32(&empty_bar[s]));
+            }
+            tc_commit(smem_u32(&tmem_full[buf]));
+          }
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    uint8_t *st = stage_base + (warp - 2) * LB_WARP_STAGE;
+    uint8_t *stG = st, *stCP = st + 4 * 4096, *stCC = stCP + 4096, *stDH = stCC + 4096, *stDC = stDH + 4096;
+    const uint32_t st_u32 = smem_u32(st);
+    int j = 0;
+    for (int t = L - 1; t >= t_last; --t) {
+      const bool mma = t < L - 1;
+      for (int tile = tile_first; tile < a.tiles_m; tile += tile_step) {
+        const int m_base = tile * TILE_M + quarter * 32;
+        for (int p = 0; p < pass_count; ++p) {
+          const int pass = pass_first + p;
+          int buf = 0;
+          bool waited = false;
+          for (int sg0 = 0; sg0 < a.CWb; sg0 += 64) {
+            const int sgw = min(64, a.CWb - sg0);
+            const int ch0 = pass * a.CWb + sg0;
+            const int ppr = sgw >> 3, nchunk = sgw >> 4;
+            if (t >= 0) {
+              // ---- stage the eight operand tiles of this channel group with coalesced async copies
+              const bf16 *gbase = a.gates + (size_t)t * M * 4 * C + ch0;
+              const bf16 *ccb = a.c_all + (size_t)t * M * C + ch0;
+              const bf16 *cpb = t > 0 ? a.c_all + (size_t)(t - 1) * M * C + ch0 : (a.c0 ? a.c0 + ch0 : nullptr);
+              const bf16 *dhb = a.dh ? a.dh + (size_t)t * M * C + ch0 : nullptr;
+              const bf16 *dcb = t == L - 1 ? (a.dc_last ? a.dc_last + ch0 : nullptr) : a.dc_ws + ch0;
+              for (int q = lane; q < 32 * ppr; q += 32) {
+                const int row = q / ppr, c16 = q - row * ppr;
+                const int m = m_base + row;
+                const bool ok = m < M;
+                const size_t mo = ok ? (size_t)m : 0;
+                const uint32_t off = row * 128 + ((c16 ^ (row & 7)) << 4);
+                const bf16 *gsrc = gbase + mo * 4 * C + c16 * 8;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) cp_async16(st_u32 + g * 4096 + off, gsrc + (size_t)g * C, ok);
+                cp_async16(st_u32 + 4 * 4096 + off, cpb ? (const void *)(cpb + mo * C + c16 * 8) : (const void *)a.gates, ok && cpb);
+                cp_async16(st_u32 + 5 * 4096 + off, ccb + mo * C + c16 * 8, ok);
+                cp_async16(st_u32 + 6 * 4096 + off, dhb ? (const void *)(dhb + mo * C + c16 * 8) : (const void *)a.gates, ok && dhb);
+                cp_async16(st_u32 + 7 * 4096 + off, dcb ? (const void *)(dcb + mo * C + c16 * 8) : (const void *)a.gates, ok && dcb);
+              }
+              asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            if (mma && !waited) {
+              buf = j & 1;
+              mbar_wait(smem_u32(&tmem_full[buf]), (j >> 1) & 1);
+              tc_fence_after();
+              waited = true;
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 256 + sg0);
+            const uint32_t rowoff = lane * 128;
+            const int sw = lane & 7;
+            for (int cc = 0; cc < nchunk; ++cc) {
+              float dhn[16];
+              if (mma) {
+                uint32_t r[16];
+                tmem_ld16(trow + (uint32_t)(cc * 16), r);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) dhn[e] = __uint_as_float(r[e]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) dhn[e] = 0.f;
+              }
+              const uint32_t o0 = rowoff + (((2 * cc) ^ sw) << 4), o1 = rowoff + (((2 * cc + 1) ^ sw) << 4);
+              if (t < 0) {   // gradient w.r.t. h0: just the GEMM result
+                uint32_t w[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  __nv_bfloat162 v = __floats2bfloat162_rn(dhn[2 * e], dhn[2 * e + 1]);
+                  w[e] = *reinterpret_cast<uint32_t *>(&v);
+                }
+                *reinterpret_cast<uint4 *>(stDH + o0) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4 *>(stDH + o1) = make_uint4(w[4], w[5], w[6], w[7]);
+                continue;
+              }
+              float in[8][16];   // f, i, o, g, c_prev, c, dh_ext, dc_in
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint4 x0 = *reinterpret_cast<const uint4 *>(st + k * 4096 + o0), x1 = *reinterpret_cast<const uint4 *>(st + k * 4096 + o1);
+                const uint32_t w[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  in[k][2 * e] = __uint_as_float(w[e] << 16);
+                  in[k][2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+                }
+              }
+              uint32_t og[4][8], odc[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                float r4[4][2], rdc[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int x = 2 * e + u;
+                  const float f = in[0][x], ig = in[1][x], o = in[2][x], g = in[3][x], cp = in[4][x];
+                  const float tc = tanh_fast(in[5][x]);
+                  const float dhv = in[6][x] + dhn[x];
+                  const float dcv = fmaf(dhv * o, 1.f - tc * tc, in[7][x]);
+                  r4[0][u] = dcv * cp * f * (1.f - f);
+                  r4[1][u] = dcv * g * ig * (1.f - ig);
+                  r4[2][u] = dhv * tc * o * (1.f - o);
+                  r4[3][u] = dcv * ig * (1.f - g * g);
+                  rdc[u] = dcv * f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  __nv_bfloat162 v = __floats2bfloat162_rn(r4[k][0], r4[k][1]);
+                  og[k][e] = *reinterpret_cast<uint32_t *>(&v);
+                }
+                __nv_bfloat162 v = __floats2bfloat162_rn(rdc[0], rdc[1]);
+                odc[e] = *reinterpret_cast<uint32_t *>(&v);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                *reinterpret_cast<uint4 *>(stG + k * 4096 + o0) = make_uint4(og[k][0], og[k][1], og[k][2], og[k][3]);
+                *reinterpret_cast<uint4 *>(stG + k * 4096 + o1) = make_uint4(og[k][4], og[k][5], og[k][6], og[k][7]);
+              }
+              *reinterpret_cast<uint4 *>(stDC + o0) = make_uint4(odc[0], odc[1], odc[2], odc[3]);
+              *reinterpret_cast<uint4 *>(stDC + o1) = make_uint4(odc[4], odc[5], odc[6], odc[7]);
+            }
+            __syncwarp();
+            // ---- write dgates_t and dc (or dh0) as contiguous row segments
+            if (t >= 0) {
+              bf16 *gdb = a.dgates + (size_t)t * M * 4 * C + ch0;
+              bf16 *dcd = ((t == 0 && a.dc0) ? a.dc0 : a.dc_ws) + ch0;
+              for (int q = lane; q < 32 * ppr; q += 32) {
+                const int row = q / ppr, c16 = q - row * ppr;
+                const int m = m_base + row;
+                if (m < M) {
+                  const uint32_t off = row * 128 + ((c16 ^ (row & 7)) << 4);
+                  bf16 *gdst = gdb + (size_t)m * 4 * C + c16 * 8;
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4 *>(gdst + (size_t)g * C) = *reinterpret_cast<const uint4 *>(stG + g * 4096 + off);
+                  *reinterpret_cast<uint4 *>(dcd + (size_t)m * C + c16 * 8) = *reinterpret_cast<const uint4 *>(stDC + off);
+                }
+              }
+            } else {
+              bf16 *hd = a.dh0 + ch0;
+              for (int q = lane; q < 32 * ppr; q += 32) {
+                const int row = q / ppr, c16 = q - row * ppr;
+                const int m = m_base + row;
+                if (m < M) *reinterpret_cast<uint4 *>(hd + (size_t)m * C + c16 * 8) = *reinterpret_cast<const uint4 *>(stDH + row * 128 + ((c16 ^ (row & 7)) << 4));
+              }
+            }
+            __syncwarp();
+          }
+          if (mma) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
+            ++j;
+          }
+          if (t >= 0) {   // publish dgates_t of this (tile, pass)
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && t > t_last) {
+              unsigned *f = a.flags + (size_t)tile * L + t;
+              asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(f) : "memory");
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // 3D bf16 tensor map [d0 (contiguous), d1, d2] with element pitches ld1, ld2; box [b0, b1, 1], 128B swizzle
 int make_map3(CUtensorMap *out, const void *ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1, uint64_t ld2, uint32_t b0,
               uint32_t b1) {
@@ -1167,6 +1451,41 @@ int lstm_seq_fwd_tc(void *gates, const void *Wh, int ldw, const void *h0, const 
   LEOD_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (size_t)a.tiles_m * L, st));
   const int grid = a.split ? a.tiles_m * a.npass : std::min(a.tiles_m, num_sms());
   lstm_seq_fwd_kernel<<<grid, LS_THREADS, smem, st>>>(mH, mH0, mW, a);
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward of the whole-window recurrence (lstm_seq_bwd_kernel).  WhT: prepared [C][ldw] = rows C..2C-1 of W_l^T (K = 4C).
+int lstm_seq_bwd_tc(const void *gates, const void *c_all, const void *c0, const void *dh, const void *dc_last, void *dgates, void *dc_ws,
+                    void *dc0, void *dh0, const void *WhT, int ldw, unsigned *flags, int M, int C, int L, cudaStream_t st) {
+  LEOD_REQUIRE(C % 16 == 0 && M > 0 && L > 0, "lstm_seq_bwd_tc: bad shape M=%d C=%d L=%d", M, C, L);
+  LstmBwdArgs a;
+  a.gates = (const bf16 *)gates; a.c_all = (const bf16 *)c_all; a.c0 = (const bf16 *)c0; a.dh = (const bf16 *)dh;
+  a.dc_last = (const bf16 *)dc_last; a.dgates = (bf16 *)dgates; a.dc_ws = (bf16 *)dc_ws; a.dc0 = (bf16 *)dc0; a.dh0 = (bf16 *)dh0;
+  a.flags = flags; a.M = M; a.C = C; a.L = L;
+  // output-channel pass: the widest multiple of 16 that divides C and keeps the B stage <= 24 KB (shared-memory budget)
+  a.CWb = 0;
+  for (int cw = std::min(C, 192); cw >= 16; cw -= 16)
+    if (C % cw == 0) { a.CWb = cw; break; }
+  a.npass = C / a.CWb;
+  a.tiles_m = ceil_div(M, TILE_M);
+  a.split = (a.npass > 1 && a.tiles_m * a.npass <= num_sms()) ? 1 : 0;
+  a.nkb = ceil_div(4 * C, TILE_K);
+  const int stage_bytes = A_STAGE_BYTES + (int)round_up(a.CWb * TILE_K * 2, 1024);
+  a.stages = std::max(2, std::min(4, (int)((224 * 1024 - 4 * LB_WARP_STAGE - 2048) / stage_bytes)));
+  CUtensorMap mG, mW;
+  LEOD_TRY(make_map3(&mG, dgates, 4 * C, M, L, 4 * C, (uint64_t)M * 4 * C, TILE_K, TILE_M));
+  LEOD_TRY(make_map(&mW, WhT, 4 * C, C, ldw, TILE_K, a.CWb));
+  const size_t smem = (size_t)a.stages * stage_bytes + 4 * LB_WARP_STAGE + 1024 + (2 * a.stages + 4) * 8 + 64;
+  LEOD_REQUIRE(smem <= 227 * 1024, "lstm_seq_bwd_tc: shared memory %zu", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LEOD_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+    attr_set = true;
+  }
+  LEOD_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (size_t)a.tiles_m * L, st));
+  const int grid = a.split ? a.tiles_m * a.npass : std::min(a.tiles_m, num_sms());
+  lstm_seq_bwd_kernel<<<grid, LS_THREADS, smem, st>>>(mG, mW, a);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
