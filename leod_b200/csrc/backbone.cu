@@ -2,6 +2,7 @@
 // the per-step kernel schedule (forward and backward of one timestep over the four stages).
 // Reference semantics: models/detection/recurrent_backbone/maxvit_rnn.py:97-115, 182-201.
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -82,7 +83,8 @@ struct leod_backbone {
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned *seq_flags = nullptr;  // per-(tile, timestep) arrival counters of the fused recurrence kernels
-  int fused_lstm = 1;        // set for the duration of a sequence-mode forward/backward pair
+  int fused_lstm = 1;
+  int fused_bwd_min_tiles = 40;   // LEOD_FUSED_LSTM_BWD_MIN_TILES overrides (tests force the fused kernel onto small stages)        // set for the duration of a sequence-mode forward/backward pair
   size_t esz() const { return cfg.dtype == LEOD_BF16 ? 2 : 4; }
   int gemm_impl = 0;  // 0 SIMT, 1 tensor core (bf16 only)
 };
@@ -471,6 +473,8 @@ static int backbone_create_impl(const leod_backbone_cfg *cfg, leod_backbone_t **
   leod_backbone *h = new leod_backbone();
   h->cfg = *cfg;
   h->gemm_impl = (cfg->dtype == LEOD_BF16) ? 1 : 0;
+  if (const char *ev = getenv("LEOD_FUSED_LSTM_BWD_MIN_TILES")) h->fused_bwd_min_tiles = atoi(ev);
+  if (const char *ev = getenv("LEOD_FUSED_LSTM")) h->fused_lstm = atoi(ev);
   int Hi = cfg->in_h, Wi = cfg->in_w, Cin = cfg->in_channels;
   for (int s = 0; s < 4; ++s) {
     StageD &d = h->d[s];
@@ -819,7 +823,7 @@ extern "C" int leod_backbone_seq_bwd(leod_backbone_t *h, const void *x, int x_dt
     // The fused backward recurrence re-streams a 128 x 4C operand tile per step and CTA: it wins while there are enough
     // token tiles to fill the GPU (measured: stages 1-2 of RVT-S at B=8); small late stages keep per-step launches, whose
     // GEMMs spread one timestep over ~120 CTAs.
-    if (h->cfg.dtype == LEOD_BF16 && h->gemm_impl == 1 && h->fused_lstm && C % 16 == 0 && M >= 40 * 128) {
+    if (h->cfg.dtype == LEOD_BF16 && h->gemm_impl == 1 && h->fused_lstm && C % 16 == 0 && M >= (int64_t)h->fused_bwd_min_tiles * 128) {
       ProfScope ps(PK_LSTM, 2.0 * M * L * 4 * C * C + 30.0 * M * L * C, 13.0 * M * L * C * e, st, (int)M, (int)C, -L);
       const bool want_dh0 = h0 && h0[s] && dh0 && dh0[s];
       LEOD_TRY(lstm_seq_bwd_tc(b.gates, cs, c0 ? c0[s] : nullptr, dh_ext, dc_last ? dc_last[s] : nullptr, g.dgates, h->ws_dcc[s],

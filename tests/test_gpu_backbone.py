@@ -118,13 +118,14 @@ def test_backbone_gradients_smooth_loss_vs_oracle(net, dtype, impl):
 
 
 @pytest.mark.parametrize('dtype', ['fp32', 'bf16'])
-def test_sequence_kernel_equals_per_step_calls(net, dtype):
+def test_sequence_kernel_equals_per_step_calls(net, dtype, monkeypatch):
     """forward_sequence (one library call per BPTT window, stage-major schedule: everything but the hidden-state half
     of the ConvLSTM batched over time, deferred weight gradients) against L calls of the per-timestep interface: same
     features, same final states, same parameter and initial-state gradients — also when the window starts from a
     carried state.  bf16: the sequence path rounds the input half of the gates to bf16 before adding the hidden half
     (one extra rounding per gate), hence the looser bound."""
     z, cfg, sd, d = net
+    monkeypatch.setenv('LEOD_FUSED_LSTM_BWD_MIN_TILES', '0')   # fused backward recurrence (incl. the dh0 iteration) on all stages
     m = build(cfg, sd, (d['H'], d['W']), dtype).train()
     bb = m.backbone
     x = torch.from_numpy(z['x']).cuda()
@@ -331,12 +332,15 @@ def test_full_size_matches_oracle(size, dataset, B):
             assert rel_err(states_seq[s - 1][1].float(), states[s - 1][1].float()) < (1e-4 if dtype == 'fp32' else 3e-2), ('seq c', dtype, s)
 
 
-@pytest.mark.parametrize('size,dataset,B,L', [('base', 'gen4', 1, 3), ('tiny', 'gen1', 2, 4)])
-def test_full_size_sequence_backward_equals_per_step(size, dataset, B, L):
+@pytest.mark.parametrize('size,dataset,B,L,force_fused_bwd', [('base', 'gen4', 1, 3, False), ('tiny', 'gen1', 2, 4, False),
+                                                             ('base', 'gen4', 1, 3, True), ('small', 'gen1', 2, 3, True)])
+def test_full_size_sequence_backward_equals_per_step(size, dataset, B, L, force_fused_bwd, monkeypatch):
     """Full-size bf16 training windows: forward_sequence + backward (batched stages, fused recurrence, deferred and
     multi-stream weight gradients) against the per-timestep calls — parameter gradients of the whole backbone."""
     from leod_b200.config import DATASETS, make_model_cfg
     from leod_b200.models.detection.yolox_extension.models.detector import YoloXDetector
+    if force_fused_bwd:   # the fused backward recurrence on every stage (multi-pass and cross-CTA split modes included)
+        monkeypatch.setenv('LEOD_FUSED_LSTM_BWD_MIN_TILES', '0')
     torch.manual_seed(1)
     fh, fw = DATASETS[dataset]['frame_hw']
     x = ((torch.rand(L, B, 20, fh, fw) < 0.1).float() * torch.randint(1, 6, (L, B, 20, fh, fw))).to(torch.uint8).cuda()
