@@ -406,7 +406,16 @@ def main():
             roof = {'bound': 'hbm', 'achieved': gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': gbs / hbm_peak}
         else:
             roof = {'bound': 'tensor', 'achieved': tfs, 'peak': tf_peak, 'unit': 'TFLOP/s', 'frac': tfs / tf_peak}
-        roof.update({'traffic': None, 'kernel': dom, 'launches_per_step': d['launches'], 'avg_launch_us': avg_ms * 1e3,
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes per launch of the same kernel class from the committed ncu capture (profiles/)
+            tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01_gemm_nt_traffic.json')))
+            if dom == 'gemm_nt':
+                traffic = tj['dram_bytes_read_per_launch'] + tj['dram_bytes_write_per_launch']
+                traffic_src = 'profiles/r01_gemm_nt_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch)'
+        except Exception:
+            pass
+        roof.update({'traffic': traffic, 'traffic_source': traffic_src, 'algorithmic_bytes_per_launch': d['bytes'] / max(d['launches'], 1),
+                     'kernel': dom, 'launches_per_step': d['launches'], 'avg_launch_us': avg_ms * 1e3,
                      'peak_source': src, 'share_of_kernel_time': d['ms'] / max(sum(k['ms'] for k in kinds.values()), 1e-9),
                      'classes_ms_per_step': {k: round(v['ms'], 3) for k, v in kinds.items()}})
         if args.profile_kinds:
