@@ -127,7 +127,7 @@ int leod_backbone_set_gemm_impl(leod_backbone_t *h, int impl);
  * C[M,N] = epilogue(A[M,K] * B[N,K]^T + bias).  A may be split in two sources along K
  * (A for k < K1, A2 for k >= K1; pass A2 = NULL, K1 = K otherwise).  dtype: operand/output type.
  * impl: 0 = SIMT fp32-accumulate kernel, 1 = tcgen05/TMA tensor-core kernel (LEOD_BF16 only).
- * epi: 0 none, 1 C=gelu(v), aux=v   2 C = R + v   3 C = v * gelu'(aux). */
+ * epi: 0 none, 1 C = gelu(v), aux = gelu'(v)   2 C = R + v   3 C = v * aux  (the backward of 1, fed with its aux). */
 int leod_gemm_nt(int impl, int dtype, const void *A, int lda, const void *A2, int lda2, int K1, const void *B, int ldb,
                  void *C, int ldc, int M, int N, int K, const float *bias, int epi, const void *R, int ldr, void *aux,
                  int ldaux, void *stream);

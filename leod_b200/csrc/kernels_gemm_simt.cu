@@ -12,15 +12,15 @@ __device__ __forceinline__ void epilogue_store(const GemmNT &g, int m, int n, fl
   if (g.bias) v += g.bias[n];
   T *C = (T *)g.C;
   switch (g.epi) {
-    case EPI_GELU:
-      ((T *)g.aux)[(size_t)m * g.ldaux + n] = from_f<T>(v);
+    case EPI_GELU:   // aux receives gelu'(v): the backward epilogue is then a plain multiply
+      ((T *)g.aux)[(size_t)m * g.ldaux + n] = from_f<T>(gelu_grad_f(v));
       v = gelu_f(v);
       break;
     case EPI_RESID:
       v += to_f<T>(((const T *)g.R)[(size_t)m * g.ldr + n]);
       break;
     case EPI_GELU_BWD:
-      v *= gelu_grad_f(to_f<T>(((const T *)g.aux)[(size_t)m * g.ldaux + n]));
+      v *= to_f<T>(((const T *)g.aux)[(size_t)m * g.ldaux + n]);
       break;
     default:
       break;

@@ -130,7 +130,7 @@ struct NtArgs {
 
 // epilogue warps: a multiple of 4 (one TMEM lane quarter each); the column range of a tile is split between the warps that
 // share a quarter.  The GELU epilogues are instruction-bound (erf + two outputs), so they get more warps.
-template <int EPI> struct NtEpiWarps { static constexpr int value = (EPI == EPI_GELU || EPI == EPI_GELU_BWD) ? 12 : 8; };
+template <int EPI> struct NtEpiWarps { static constexpr int value = EPI == EPI_GELU ? 12 : 8; };
 template <int EPI> struct NtStageBytes { static constexpr int value = EPI == EPI_GELU ? 8192 : 4096; };   // per epilogue warp
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -163,7 +163,7 @@ __device__ __forceinline__ void nt_epilogue_chunk(const GemmNT &g, const uint32_
       __align__(16) bf16 t[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        t[j] = __float2bfloat16_rn(v[j]);
+        t[j] = __float2bfloat16_rn(gelu_grad_f(v[j]));
         v[j] = gelu_f(v[j]);
       }
       ((uint4 *)ax)[0] = ((uint4 *)t)[0];
@@ -181,7 +181,7 @@ __device__ __forceinline__ void nt_epilogue_chunk(const GemmNT &g, const uint32_
       ((uint4 *)t)[0] = ((const uint4 *)ax)[0];
       ((uint4 *)t)[1] = ((const uint4 *)ax)[1];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] *= gelu_grad_f(__bfloat162float(t[j]));
+      for (int j = 0; j < 16; ++j) v[j] *= __bfloat162float(t[j]);
     }
     __align__(16) bf16 o[16];
 #pragma unroll
@@ -193,12 +193,12 @@ __device__ __forceinline__ void nt_epilogue_chunk(const GemmNT &g, const uint32_
     for (int j = 0; j < nvalid; ++j) {
       float x = v[j];
       if (g.epi == EPI_GELU) {
-        ((bf16 *)g.aux)[(size_t)m * g.ldaux + n + j] = __float2bfloat16_rn(x);
+        ((bf16 *)g.aux)[(size_t)m * g.ldaux + n + j] = __float2bfloat16_rn(gelu_grad_f(x));
         x = gelu_f(x);
       } else if (g.epi == EPI_RESID) {
         x += __bfloat162float(((const bf16 *)g.R)[(size_t)m * g.ldr + n + j]);
       } else if (g.epi == EPI_GELU_BWD) {
-        x *= gelu_grad_f(__bfloat162float(((const bf16 *)g.aux)[(size_t)m * g.ldaux + n + j]));
+        x *= __bfloat162float(((const bf16 *)g.aux)[(size_t)m * g.ldaux + n + j]);
       }
       ((bf16 *)g.C)[(size_t)m * g.ldc + n + j] = __float2bfloat16_rn(x);
     }
@@ -250,11 +250,15 @@ __device__ __forceinline__ void nt_epilogue_compute(const GemmNT &g, const uint3
   if (EPI == EPI_GELU) {
     uint32_t *tw = reinterpret_cast<uint32_t *>(t);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const __nv_bfloat162 pr = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    for (int j = 0; j < 8; ++j) {   // gelu and gelu' share erf and exp: aux gets the derivative, the backward is a multiply
+      float c0, e0, c1, e1;
+      gelu_parts_fast(v[2 * j], c0, e0);
+      gelu_parts_fast(v[2 * j + 1], c1, e1);
+      const __nv_bfloat162 pr = __floats2bfloat162_rn(fmaf(v[2 * j] * 0.39894228040143267794f, e0, c0),
+                                                      fmaf(v[2 * j + 1] * 0.39894228040143267794f, e1, c1));
       tw[j] = *reinterpret_cast<const uint32_t *>(&pr);
-      v[2 * j] = gelu_fast(v[2 * j]);
-      v[2 * j + 1] = gelu_fast(v[2 * j + 1]);
+      v[2 * j] *= c0;
+      v[2 * j + 1] *= c1;
     }
   } else if (EPI == EPI_RESID) {
     if (row_ok) {
@@ -274,8 +278,8 @@ __device__ __forceinline__ void nt_epilogue_compute(const GemmNT &g, const uint3
       const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        v[2 * j] *= gelu_grad_fast(__uint_as_float(w[j] << 16));
-        v[2 * j + 1] *= gelu_grad_fast(__uint_as_float(w[j] & 0xffff0000u));
+        v[2 * j] *= __uint_as_float(w[j] << 16);
+        v[2 * j + 1] *= __uint_as_float(w[j] & 0xffff0000u);
       }
     }
   }
@@ -1374,7 +1378,7 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   const int stage_bytes = A_STAGE_BYTES + a.BN * TILE_K * 2;
   const int total_kb = a.nkb * ceil_div(a.tiles_m * a.tiles_n, num_sms());
   a.staged = (g.N % 16 == 0 && (((uintptr_t)g.bias) & 15) == 0) ? 1 : 0;
-  const bool gelu_like = a.staged && (g.epi == EPI_GELU || g.epi == EPI_GELU_BWD);
+  const bool gelu_like = a.staged && g.epi == EPI_GELU;
   const int epi_warps = gelu_like ? NtEpiWarps<EPI_GELU>::value : 8;
   const int epi_bytes = epi_warps * ((a.staged && g.epi == EPI_GELU) ? 8192 : 4096) + 256;
   a.stages = std::min(std::min(4, (int)((224 * 1024 - epi_bytes - 2048) / stage_bytes)), std::max(total_kb, 1));
