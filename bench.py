@@ -358,6 +358,9 @@ def main():
             copied[slot].record(copy_stream)
     for c in consumed:
         c.record()
+    first_dev = [h[2].to(dev) for h in host]
+    loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    read_ev = [torch.cuda.Event() for _ in range(2)]
     barrier()
     e0.record()
     issue_copy(0)
@@ -367,9 +370,17 @@ def main():
             issue_copy(i + 1)
         torch.cuda.current_stream().wait_event(copied[slot])
         _, lab, first = host[i % n_batches]
-        loss = train_step(dev_buf[slot], lab, first.to(dev, non_blocking=True))
+        loss = train_step(dev_buf[slot], lab, first_dev[i % n_batches])
         consumed[slot].record()
-        loss_host = float(loss.detach())              # device -> host read of the step's result
+        # device -> host read of every step's result, one step late (as an asynchronous logger does) so that the host
+        # keeps enqueuing the next step while this one runs; the last one is read before the region closes
+        loss_pinned[i % 2].copy_(loss.detach(), non_blocking=True)
+        read_ev[i % 2].record()
+        if i > 0:
+            read_ev[(i - 1) % 2].synchronize()
+            loss_host = float(loss_pinned[(i - 1) % 2])
+    read_ev[(args.steps - 1) % 2].synchronize()
+    loss_host = float(loss_pinned[(args.steps - 1) % 2])
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)

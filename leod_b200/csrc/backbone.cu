@@ -84,7 +84,7 @@ struct leod_backbone {
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   unsigned *seq_flags = nullptr;  // per-(tile, timestep) arrival counters of the fused recurrence kernels
   int fused_lstm = 1;
-  int fused_bwd_min_tiles = 40;   // LEOD_FUSED_LSTM_BWD_MIN_TILES overrides (tests force the fused kernel onto small stages)        // set for the duration of a sequence-mode forward/backward pair
+  int fused_bwd_min_tiles = 0;    // LEOD_FUSED_LSTM_BWD_MIN_TILES: stages with fewer 128-token tiles use per-step launches        // set for the duration of a sequence-mode forward/backward pair
   size_t esz() const { return cfg.dtype == LEOD_BF16 ? 2 : 4; }
   int gemm_impl = 0;  // 0 SIMT, 1 tensor core (bf16 only)
 };
@@ -820,9 +820,8 @@ extern "C" int leod_backbone_seq_bwd(leod_backbone_t *h, const void *x, int x_dt
     // external gradient w.r.t. h_all[s], all timesteps: the caller's (head) gradient, plus - for s < 3 - the gradient
     // through stage s+1's downsample, which front_bwd(s+1) has already added into ws_hint
     const char *dh_ext = s < 3 ? (const char *)h->ws_hint : ((dh_all && dh_all[s]) ? (const char *)dh_all[s] : nullptr);
-    // The fused backward recurrence re-streams a 128 x 4C operand tile per step and CTA: it wins while there are enough
-    // token tiles to fill the GPU (measured: stages 1-2 of RVT-S at B=8); small late stages keep per-step launches, whose
-    // GEMMs spread one timestep over ~120 CTAs.
+    // The fused backward recurrence re-streams a 128 x 4C operand tile per step and CTA; stages with few token tiles are
+    // split over output channels so that ~120 CTAs share a timestep (lstm_seq_bwd_tc).
     if (h->cfg.dtype == LEOD_BF16 && h->gemm_impl == 1 && h->fused_lstm && C % 16 == 0 && M >= (int64_t)h->fused_bwd_min_tiles * 128) {
       ProfScope ps(PK_LSTM, 2.0 * M * L * 4 * C * C + 30.0 * M * L * C, 13.0 * M * L * C * e, st, (int)M, (int)C, -L);
       const bool want_dh0 = h0 && h0[s] && dh0 && dh0[s];

@@ -1467,12 +1467,14 @@ int lstm_seq_bwd_tc(const void *gates, const void *c_all, const void *c0, const 
   a.gates = (const bf16 *)gates; a.c_all = (const bf16 *)c_all; a.c0 = (const bf16 *)c0; a.dh = (const bf16 *)dh;
   a.dc_last = (const bf16 *)dc_last; a.dgates = (bf16 *)dgates; a.dc_ws = (bf16 *)dc_ws; a.dc0 = (bf16 *)dc0; a.dh0 = (bf16 *)dh0;
   a.flags = flags; a.M = M; a.C = C; a.L = L;
-  // output-channel pass: the widest multiple of 16 that divides C and keeps the B stage <= 24 KB (shared-memory budget)
-  a.CWb = 0;
-  for (int cw = std::min(C, 192); cw >= 16; cw -= 16)
-    if (C % cw == 0) { a.CWb = cw; break; }
-  a.npass = C / a.CWb;
+  // output-channel pass: the widest multiple of 16 that divides C and keeps the B stage <= 24 KB (shared-memory budget);
+  // stages with few token tiles are split into more, narrower passes so that ~120 CTAs share a timestep
   a.tiles_m = ceil_div(M, TILE_M);
+  const int want_pass = a.tiles_m >= 40 ? 1 : ceil_div(120, a.tiles_m);
+  a.CWb = 16;
+  for (int cw = std::min(C, 192); cw >= 16; cw -= 16)
+    if (C % cw == 0 && C / cw >= want_pass) { a.CWb = cw; break; }
+  a.npass = C / a.CWb;
   a.split = (a.npass > 1 && a.tiles_m * a.npass <= num_sms()) ? 1 : 0;
   a.nkb = ceil_div(4 * C, TILE_K);
   const int stage_bytes = A_STAGE_BYTES + (int)round_up(a.CWb * TILE_K * 2, 1024);

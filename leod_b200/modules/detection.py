@@ -25,6 +25,14 @@ except Exception:  # noqa: BLE001
     _Base = nn.Module
 
 
+def _h2d_async(t: torch.Tensor, device) -> torch.Tensor:
+    """Small host tensor -> device through pinned memory, without blocking the host on the stream's pending work (a
+    pageable copy is host-synchronous and would serialise the host behind the previous training step)."""
+    if t.is_cuda or torch.device(device).type != 'cuda':
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 def get_subsample_label_idx(L: int, use_every: int = -1, remove_every: int = -1):
     """modules/utils/ssod.py:19-37."""
     assert use_every == -1 or remove_every == -1
@@ -80,9 +88,11 @@ class Module(_Base):
         ignore = self.mdl_config.get('ignore_image', False)
         ignore_label = self.mdl_config.head.get('ignore_label', 1024)
         if self.use_sequence_kernel:
-            # the time loop of modules/detection.py:188-224 runs inside the library (one call per window)
+            # the time loop of modules/detection.py:188-224 runs inside the library (one call per window).  Everything
+            # that touches the host (label lists, index tensors, their host->device copies) is prepared BEFORE the
+            # window is enqueued: a pageable copy issued afterwards would block the host until the backbone has finished
+            # and leave the GPU idle while the head is being set up.
             ev = ev_seq if torch.is_tensor(ev_seq) else torch.stack(list(ev_seq))
-            feats_all, prev_states = self.mdl.backbone.forward_sequence(ev, prev_states)
             t_idx, b_idx = [], []
             for tidx in range(L):
                 current_labels, valid_idx = sparse_obj_labels[tidx].get_valid_labels_and_batch_indices(
@@ -92,8 +102,11 @@ class Module(_Base):
                     t_idx.extend([tidx] * len(valid_idx))
                     b_idx.extend(valid_idx)
             assert len(obj_labels) > 0
-            ti = torch.as_tensor(t_idx, device=ev.device)
-            bi = torch.as_tensor(b_idx, device=ev.device)
+            ti = _h2d_async(torch.as_tensor(t_idx), ev.device)
+            bi = _h2d_async(torch.as_tensor(b_idx), ev.device)
+            labels_yolox = type(obj_labels[0]).get_labels_as_batched_tensor(obj_label_list=obj_labels, format_='yolox')
+            labels_yolox = _h2d_async(labels_yolox.to(torch.float32), ev.device)
+            feats_all, prev_states = self.mdl.backbone.forward_sequence(ev, prev_states)
             sel = {k: v[ti, bi] for k, v in feats_all.items() if k in self.mdl.fpn.in_features}
         else:
             selector = BackboneFeatureSelector()
@@ -108,8 +121,9 @@ class Module(_Base):
             sel = selector.get_batched_backbone_features()
         self.mode_2_rnn_states[mode].save_states_and_detach(worker_id=worker_id, states=prev_states)
         assert len(obj_labels) > 0
-        labels_yolox = type(obj_labels[0]).get_labels_as_batched_tensor(obj_label_list=obj_labels, format_='yolox')
-        labels_yolox = labels_yolox.to(device=ev_seq[0].device, dtype=torch.float32)
+        if not self.use_sequence_kernel:
+            labels_yolox = type(obj_labels[0]).get_labels_as_batched_tensor(obj_label_list=obj_labels, format_='yolox')
+            labels_yolox = labels_yolox.to(device=ev_seq[0].device, dtype=torch.float32)
         predictions, losses = self.mdl.forward_detect(backbone_features=sel, targets=labels_yolox)
         assert losses is not None and 'loss' in losses
         out = {'loss': losses['loss']}

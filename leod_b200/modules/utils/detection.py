@@ -64,7 +64,13 @@ class RNNStates:
                 inp[:] = 0
             else:
                 assert len(indices_or_bool_tensor) > 0
-                inp[indices_or_bool_tensor] = 0
+                idx = indices_or_bool_tensor
+                if th.is_tensor(idx) and idx.dtype == th.bool:
+                    # same rows zeroed as `inp[mask] = 0`, without the device->host round trip of boolean indexing
+                    # (which would stall the host on the previous step's GPU work at the start of every step)
+                    inp.masked_fill_(idx.to(inp.device).view(-1, *([1] * (inp.dim() - 1))), 0)
+                else:
+                    inp[idx] = 0
             return inp
         if isinstance(inp, (list, tuple)):
             return type(inp)(cls.recursive_reset(x, indices_or_bool_tensor) for x in inp)
