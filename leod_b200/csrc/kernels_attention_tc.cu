@@ -108,18 +108,20 @@ template <int TP, int DH, int DHP, int LDQ, int NTHREADS, bool WITH_DO>
 __device__ __forceinline__ void stage_qkv(const bf16 *__restrict__ qkv, const bf16 *__restrict__ dout, bf16 *sQ, bf16 *sK, bf16 *sV,
                                           bf16 *sdO, const int *rows, int T, int C, int head, int tid) {
   constexpr int VPR = DH / 8, VPP = DHP / 8, NM = WITH_DO ? 4 : 3;
+  // asynchronous 16-byte copies (zero-filled where padded): every load of the CTA is in flight at once instead of one
+  // dependent load -> store pair per loop iteration
   for (int idx = tid; idx < TP * NM * VPP; idx += NTHREADS) {
     const int t = idx / (NM * VPP), rem = idx % (NM * VPP), which = rem / VPP, v8 = rem % VPP;
-    uint4 val = make_uint4(0u, 0u, 0u, 0u);
-    if (t < T && v8 < VPR) {
-      if (which < 3)
-        val = *reinterpret_cast<const uint4 *>(qkv + (size_t)rows[t] * 3 * C + head * 3 * DH + which * DH + v8 * 8);
-      else
-        val = *reinterpret_cast<const uint4 *>(dout + (size_t)rows[t] * C + head * DH + v8 * 8);
-    }
+    const bool ok = t < T && v8 < VPR;
+    const bf16 *src = qkv;
+    if (ok) src = which < 3 ? qkv + (size_t)rows[t] * 3 * C + head * 3 * DH + which * DH + v8 * 8
+                            : dout + (size_t)rows[t] * C + head * DH + v8 * 8;
     bf16 *dst = which == 0 ? sQ : (which == 1 ? sK : (which == 2 ? sV : sdO));
-    *reinterpret_cast<uint4 *>(&dst[t * LDQ + v8 * 8]) = val;
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr(&dst[t * LDQ + v8 * 8])), "l"(src), "r"(sz) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // NT_S: 8-column tiles of the score matrix; NT_O: dh / 8; KS: ceil(dh / 16)

@@ -1431,11 +1431,17 @@ int lstm_seq_fwd_tc(void *gates, const void *Wh, int ldw, const void *h0, const 
   LstmSeqArgs a;
   a.gates = (bf16 *)gates; a.c0 = (const bf16 *)c0; a.h_all = (bf16 *)h_all; a.c_all = (bf16 *)c_all; a.flags = flags;
   a.M = M; a.C = C; a.L = L;
-  a.CW = 0;
-  for (int cw = 64; cw >= 16; cw -= 16)
-    if (C % cw == 0) { a.CW = cw; break; }
-  a.npass = C / a.CW;
+  // channel pass: <= 64 channels (4 gates x 64 = 256 accumulator columns); stages with few token tiles are split into
+  // more, narrower passes so that ~120 CTAs share a timestep
   a.tiles_m = ceil_div(M, TILE_M);
+  const int want_pass = a.tiles_m >= 40 ? 1 : ceil_div(120, a.tiles_m);
+  a.CW = 16;
+  for (int cw = 64; cw >= 16; cw -= 16)
+    if (C % cw == 0 && C / cw >= want_pass) { a.CW = cw; break; }
+  if (a.tiles_m * (C / a.CW) > num_sms())   // the narrow split only pays when every (tile, pass) gets its own CTA
+    for (int cw = 64; cw >= 16; cw -= 16)
+      if (C % cw == 0) { a.CW = cw; break; }
+  a.npass = C / a.CW;
   a.split = (a.npass > 1 && a.tiles_m * a.npass <= num_sms()) ? 1 : 0;
   a.has_h0 = h0 != nullptr;
   a.nkb = ceil_div(C, TILE_K);
@@ -1474,6 +1480,9 @@ int lstm_seq_bwd_tc(const void *gates, const void *c_all, const void *c0, const 
   a.CWb = 16;
   for (int cw = std::min(C, 192); cw >= 16; cw -= 16)
     if (C % cw == 0 && C / cw >= want_pass) { a.CWb = cw; break; }
+  if (a.tiles_m * (C / a.CWb) > num_sms())
+    for (int cw = std::min(C, 192); cw >= 16; cw -= 16)
+      if (C % cw == 0) { a.CWb = cw; break; }
   a.npass = C / a.CWb;
   a.split = (a.npass > 1 && a.tiles_m * a.npass <= num_sms()) ? 1 : 0;
   a.nkb = ceil_div(4 * C, TILE_K);
