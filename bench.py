@@ -252,6 +252,8 @@ def main():
     ap.add_argument('--profile-csv', default=None, help='write one line per launch of the roofline pass to this CSV')
     ap.add_argument('--workload', default='train', choices=['train', 'sweep'],
                     help='train: BASELINE configs[1] (the headline metric); sweep: teacher pseudo-label sweep, configs[3] shape')
+    ap.add_argument('--e2e-lag', type=int, default=2, help='the loss of step i is read back on the host after step i+lag was enqueued')
+    ap.add_argument('--copy-streams', type=int, default=4, help='streams the per-step host->device upload is split over (e2e leg)')
     ap.add_argument('--no-graph-head', action='store_true', help='run neck/head/loss eagerly instead of replaying a CUDA graph')
     ap.add_argument('--phases', action='store_true', help='after the timed regions, time the phases of 3 extra steps (stderr)')
     args = ap.parse_args()
@@ -326,8 +328,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    h0 = time.perf_counter()
     for i in range(args.steps):
         loss = train_step(*resident[i % n_batches])
+    host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / args.steps     # host time to enqueue one step (no sync inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -345,22 +349,28 @@ def main():
     # on a copy stream before step i computes (double buffering, as a prefetching input pipeline does), and the loss
     # of every step is read back to the host.
     h2d = host[0][0].numel()
-    copy_stream = torch.cuda.Stream()
+    NCOPY = args.copy_streams     # the upload is split along L over several streams (one DMA engine does not fill the link)
+    copy_streams = [torch.cuda.Stream() for _ in range(NCOPY)]
     dev_buf = [torch.empty_like(host[0][0], device=dev) for _ in range(2)]
-    copied = [torch.cuda.Event() for _ in range(2)]
+    copied = [[torch.cuda.Event() for _ in range(NCOPY)] for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+    bounds = [L * c // NCOPY for c in range(NCOPY + 1)]
 
     def issue_copy(i):
         slot = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])         # the step that last read this buffer has finished
-            dev_buf[slot].copy_(host[i % n_batches][0], non_blocking=True)
-            copied[slot].record(copy_stream)
+        src = host[i % n_batches][0]
+        for c, cs in enumerate(copy_streams):
+            with torch.cuda.stream(cs):
+                cs.wait_event(consumed[slot])             # the step that last read this buffer has finished
+                dev_buf[slot][bounds[c]:bounds[c + 1]].copy_(src[bounds[c]:bounds[c + 1]], non_blocking=True)
+                copied[slot][c].record(cs)
     for c in consumed:
         c.record()
     first_dev = [h[2].to(dev) for h in host]
-    loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    read_ev = [torch.cuda.Event() for _ in range(2)]
+    lag = max(0, args.e2e_lag)
+    NLAG = lag + 1
+    loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(NLAG)]
+    read_ev = [torch.cuda.Event() for _ in range(NLAG)]
     barrier()
     e0.record()
     issue_copy(0)
@@ -368,19 +378,21 @@ def main():
         slot = i % 2
         if i + 1 < args.steps:
             issue_copy(i + 1)
-        torch.cuda.current_stream().wait_event(copied[slot])
+        for ev_c in copied[slot]:
+            torch.cuda.current_stream().wait_event(ev_c)
         _, lab, first = host[i % n_batches]
         loss = train_step(dev_buf[slot], lab, first_dev[i % n_batches])
         consumed[slot].record()
-        # device -> host read of every step's result, one step late (as an asynchronous logger does) so that the host
-        # keeps enqueuing the next step while this one runs; the last one is read before the region closes
-        loss_pinned[i % 2].copy_(loss.detach(), non_blocking=True)
-        read_ev[i % 2].record()
-        if i > 0:
-            read_ev[(i - 1) % 2].synchronize()
-            loss_host = float(loss_pinned[(i - 1) % 2])
-    read_ev[(args.steps - 1) % 2].synchronize()
-    loss_host = float(loss_pinned[(args.steps - 1) % 2])
+        # device -> host read of EVERY step's result, `lag` steps late (as an asynchronous logger does) so that the host
+        # keeps enqueuing work while the step runs; the outstanding ones are read before the region closes
+        loss_pinned[i % NLAG].copy_(loss.detach(), non_blocking=True)
+        read_ev[i % NLAG].record()
+        if i >= lag:
+            read_ev[(i - lag) % NLAG].synchronize()
+            loss_host = float(loss_pinned[(i - lag) % NLAG])
+    for i in range(max(0, args.steps - lag), args.steps):
+        read_ev[i % NLAG].synchronize()
+        loss_host = float(loss_pinned[i % NLAG])
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -496,7 +508,7 @@ def main():
                        'saved activations per step (>> 126 MB L2)', 'parallelism': f'dp{world}',
                        'algorithmic_tflop_per_step': algo_tflop, 'achieved_tflops': algo_tflop / (ms / args.steps * 1e-3) * world},
             'e2e': {'value': e2e_value, 'unit': 'event-frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
-            'gpu_launches': int(launches), 'roofline': roof, 'cpu_baseline': cpu, 'clocks': clocks, 'loss': loss_host}))
+            'gpu_launches': int(launches), 'host_enqueue_ms_per_step': host_enqueue_ms, 'roofline': roof, 'cpu_baseline': cpu, 'clocks': clocks, 'loss': loss_host}))
     if world > 1:
         # captured graphs hold NCCL work: drop them before tearing the process group down, and never hang at exit
         module.mdl._detect_graphs.clear()

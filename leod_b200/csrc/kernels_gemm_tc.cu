@@ -220,17 +220,6 @@ __device__ __forceinline__ void gelu_parts_fast(float x, float &cdf, float &e) {
   const float h = 0.5f * p * e;               // 0.5 * (1 - erf(|x|/sqrt2))
   cdf = x >= 0.f ? 1.0f - h : h;
 }
-__device__ __forceinline__ float gelu_fast(float x) {
-  float cdf, e;
-  gelu_parts_fast(x, cdf, e);
-  return x * cdf;
-}
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  float cdf, e;
-  gelu_parts_fast(x, cdf, e);
-  return fmaf(x * 0.39894228040143267794f, e, cdf);
-}
-
 // Same arithmetic for a full 16-column chunk, but the results stay in registers (packed bf16) so the caller can
 // stage them in shared memory and write whole 128-byte lines: o = output chunk, t = pre-GELU chunk (EPI_GELU only).
 template <int EPI>
