@@ -291,6 +291,41 @@ def gen_optim():
     print('optim_cases.npz')
 
 
+def gen_fullsize():
+    """Full-size runs of the REFERENCE itself (BASELINE configs[0]: RVT-tiny, 10 input channels, 1 x 240 x 304, one
+    frame; and the configs[1] model RVT-small at batch 1, two frames) with name-seeded weights (tests/helpers.py:
+    det_state_value), so only the small outputs are stored: stage-4 feature, final cell state of stage 4, decoded
+    predictions and the post-processed detections."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from helpers import FULLSIZE_CASES, det_events, det_fill_
+    sizes = {'tiny': (32, 32, 0.33), 'small': (48, 24, 0.33), 'base': (64, 32, 0.67)}
+    dsets = {'gen1': ((8, 10), 2, (256, 320), (240, 304)), 'gen4': ((6, 10), 3, (384, 640), (360, 640))}
+    out = {}
+    for tag, (size, dataset, inch, B, L) in FULLSIZE_CASES.items():
+        embed, dh, depth = sizes[size]
+        part, ncls, in_res, frame = dsets[dataset]
+        ref = YoloXDetector(model_cfg(embed, dh, part, ncls, depth, inch))
+        det_fill_(ref)
+        ref.eval()
+        x = det_events(7, (L, B, inch, frame[0], frame[1]))
+        xp = torch.zeros(L, B, inch, in_res[0], in_res[1])
+        xp[..., :frame[0], :frame[1]] = x.float()          # utils/padding.py:33-58
+        states = None
+        with torch.no_grad():
+            for t in range(L):
+                feats, states = ref.forward_backbone(xp[t], states)
+            preds, _ = ref.forward_detect(feats)
+            dets = postprocess(preds.clone(), ncls, 0.001, 0.45)
+        out[f'{tag}/feat4'] = feats[4].numpy()
+        out[f'{tag}/c4'] = states[3][1].numpy()
+        out[f'{tag}/preds'] = preds.numpy()
+        for b in range(B):
+            d = dets[b]
+            out[f'{tag}/det{b}'] = (d if d is not None else torch.zeros(0, 7)).numpy()
+        print(tag, 'preds', tuple(preds.shape), 'dets', [0 if d is None else len(d) for d in dets])
+    np.savez_compressed(os.path.join(HERE, 'fullsize_cases.npz'), **out)
+
+
 if __name__ == '__main__':
     torch.set_num_threads(4)
     gen_net()
@@ -298,3 +333,4 @@ if __name__ == '__main__':
     gen_pred2label()
     gen_binning()
     gen_optim()
+    gen_fullsize()

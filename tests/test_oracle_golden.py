@@ -119,3 +119,35 @@ def test_ema_and_adamw_match_reference():
     for s in range(3):
         optim.adamw_step(p, torch.from_numpy(z[f'adamw/g{s}']), m, v, s + 1, lr=2e-4, clip_value=1.0)
         np.testing.assert_allclose(p.numpy(), z[f'adamw/p{s + 1}'], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('tag', ['tiny_gen1_c10', 'small_gen1'])
+def test_full_size_oracle_matches_reference_run(tag):
+    """BASELINE configs[0] (RVT-tiny, 10 input channels, 240x304, one frame) and the configs[1] model at batch 1: the
+    oracle against outputs of the reference itself (tests/golden/make_golden.py: gen_fullsize, name-seeded weights)."""
+    from helpers import FULLSIZE_CASES, canon_rows, det_events, det_state_value
+    from leod_b200.config import DATASETS, make_model_cfg
+    from leod_b200.models.detection.yolox_extension.models.detector import YoloXDetector
+    from oracle import postprocess as opp, rvt, yolox
+    from oracle.config import ModelCfg
+    z = np.load(os.path.join(GOLDEN, 'fullsize_cases.npz'))
+    size, dataset, inch, B, L = FULLSIZE_CASES[tag]
+    torch.set_num_threads(8)
+    ocfg = ModelCfg.named(size, dataset)
+    ocfg.input_channels = inch
+    # parameter names / shapes come from the product's (reference-compatible) state dict
+    m = YoloXDetector(make_model_cfg(size=size, dataset=dataset, input_channels=inch, compute_dtype='fp32'))
+    sd = {k: det_state_value(k, v.shape).to(v.dtype) for k, v in m.state_dict().items()}
+    fh, fw = DATASETS[dataset]['frame_hw']
+    x = det_events(7, (L, B, inch, fh, fw))
+    states = None
+    with torch.no_grad():
+        for t in range(L):
+            feats, states = rvt.backbone_forward(rvt.pad_input(x[t].float(), DATASETS[dataset]['in_res_hw']), states, sd, ocfg)
+        preds = yolox.detect_forward(feats, sd, ocfg)[0]
+    assert np.abs(feats[4].numpy() - z[f'{tag}/feat4']).max() < 2e-4 * np.abs(z[f'{tag}/feat4']).max()
+    assert np.abs(states[3][1].numpy() - z[f'{tag}/c4']).max() < 2e-4 * max(1.0, np.abs(z[f'{tag}/c4']).max())
+    np.testing.assert_allclose(preds.numpy(), z[f'{tag}/preds'], rtol=2e-4, atol=2e-3)
+    dets = opp.postprocess(z[f'{tag}/preds'], ocfg.num_classes, 0.001, 0.45)
+    for b in range(B):   # anchors over the zero-padded rows produce exactly equal scores: compare order-independently there
+        np.testing.assert_allclose(canon_rows(dets[b]), canon_rows(z[f'{tag}/det{b}']), rtol=0, atol=1e-5)
