@@ -336,7 +336,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = lib.leod_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -399,6 +398,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = frames / (float(t) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions (value and e2e)
 
     # ---- roofline pass (not timed into value): CUDA events around every launch of each kernel class
     roof = None
