@@ -97,10 +97,13 @@ int leod_backbone_step_bwd(leod_backbone_t *h, const void *x, int x_dtype, int x
                            const void *const h_prev[4], const void *const c_prev[4], const void *const h_out[4],
                            const void *const c_out[4], const void *save, const void *const dh_out[4], const void *const dc_out[4],
                            void *const dh_prev[4], void *const dc_prev[4], void *stream);
-/* A whole BPTT window (L timesteps) in one call — the fast path.  Stage 1 up to its LSTM is independent of the
- * recurrent state and runs batched over all L*B frames; weight gradients are computed by one GEMM per layer over
- * all timesteps.  Activations live in a library-owned arena (leod_backbone_seq_arena_bytes), so a forward must be
- * followed by at most one backward with the same (B, L) before the next forward.
+/* A whole BPTT window (L timesteps) in one call — the fast path; replaces the time loops of modules/detection.py:188-224
+ * and modules/pseudo_labeler.py:676-704.  Stage-major schedule: stage s at time t depends only on stage s-1 at time t and on
+ * its own state at t-1, so every stage runs over all L timesteps before the next one starts; everything except the
+ * hidden-state half of the ConvLSTM is batched over the L*B frames, the recurrence itself is one persistent kernel per
+ * stage (bf16), and weight gradients are computed by one GEMM per layer over all timesteps.  Activations live in a
+ * library-owned arena (leod_backbone_seq_arena_bytes), so a forward must be followed by at most one backward with the
+ * same (B, L) before the next forward.  Results equal L calls of leod_backbone_step_fwd / _step_bwd.
  *  x      : device [L, B, in_channels, x_h, x_w], dtype x_dtype
  *  h0/c0  : initial state per stage (NHWC, storage dtype) or NULL
  *  h_all  : out, per stage [L, B, h, w, C] hidden states of every timestep (= the features)
