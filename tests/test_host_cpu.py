@@ -162,3 +162,21 @@ def test_pseudo_labeler_masks_and_hflip_batch_doubling(net):
     exp[3, 1] = exp[3, 3] = False             # ground truth present
     np.testing.assert_array_equal(pse, exp)
     assert gt.sum() == 2 and gt[3, 1] and gt[3, 3] and skipped_gt.sum() == 0
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores; runs without a GPU) prints ONE JSON line with the
+    keys the driver reads."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'event-frames/s' and d['higher_is_better'] is True
+    assert d['value'] > 0 and d['steps'] == 1 and d['n_gpus'] == 1 and d['vs_baseline'] is None
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'event-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config']
