@@ -375,13 +375,15 @@ def main():
     issue_copy(0)
     for i in range(args.steps):
         slot = i % 2
-        if i + 1 < args.steps:
-            issue_copy(i + 1)
         for ev_c in copied[slot]:
             torch.cuda.current_stream().wait_event(ev_c)
         _, lab, first = host[i % n_batches]
         loss = train_step(dev_buf[slot], lab, first_dev[i % n_batches])
         consumed[slot].record()
+        # the next batch's bulk upload is issued AFTER this step has been enqueued: the step's own small uploads (label
+        # and index tensors) would otherwise queue behind 245 MB on the host->device copy engine and stall the stream
+        if i + 1 < args.steps:
+            issue_copy(i + 1)
         # device -> host read of EVERY step's result, `lag` steps late (as an asynchronous logger does) so that the host
         # keeps enqueuing work while the step runs; the outstanding ones are read before the region closes
         loss_pinned[i % NLAG].copy_(loss.detach(), non_blocking=True)

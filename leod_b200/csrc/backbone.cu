@@ -790,7 +790,7 @@ extern "C" int leod_backbone_seq_fwd(leod_backbone_t *h, const void *x, int x_dt
   for (int s = 0; s < 4; ++s) {
     const StageD &d = h->d[s];
     const int64_t M = (int64_t)B * d.Ho * d.Wo, C = d.C;
-    LEOD_CUDA(cudaMemcpyAsync(c_last[s], (char *)h->seq_arena + (lay[s].c_all + (L - 1) * M * C) * e, M * C * e, cudaMemcpyDeviceToDevice, st));
+    LEOD_TRY(device_copy(c_last[s], (char *)h->seq_arena + (lay[s].c_all + (L - 1) * M * C) * e, (size_t)(M * C * e), st));
   }
   return 0;
 }

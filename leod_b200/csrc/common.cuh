@@ -129,6 +129,8 @@ int lstm_pointwise_fwd(int dtype, void *gates /*in: pre-act, out: activated*/, c
                        int M, int C, cudaStream_t st);
 int lstm_pointwise_bwd(int dtype, const void *gates, const void *c_prev, const void *c_out, const void *dh, const void *dh2,
                        const void *dc, void *dgates, void *dc_prev, int M, int C, cudaStream_t st, const void *dh3 = nullptr);
+int device_copy(void *dst, const void *src, size_t bytes, cudaStream_t st);   // SM-side (not copy-engine) copy
+int device_zero_u32(unsigned *p, int64_t n, cudaStream_t st);
 int add_tensors(int dtype, const void *a, const void *b, void *out, int64_t n, cudaStream_t st);
 int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin, int xh, int xw, int Hp, int Wp, int ksz,
                 int stride, int pad, int ldcol, cudaStream_t st);

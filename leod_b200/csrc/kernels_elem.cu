@@ -533,6 +533,19 @@ __global__ void ls_finalize_kernel(float *__restrict__ G, float *__restrict__ s,
 
 inline int blocks_for(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
 
+// SM-side copy / clear for small buffers on the compute stream.  cudaMemcpyAsync / cudaMemsetAsync would go to a copy
+// engine and queue behind whatever bulk host->device upload is in flight there (the next step's input batch).
+__global__ void copy_u4_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int64_t n16, const unsigned char *__restrict__ src_tail,
+                               unsigned char *__restrict__ dst_tail, int ntail) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n16) dst[i] = src[i];
+  if (i < ntail) dst_tail[i] = src_tail[i];
+}
+__global__ void zero_u32_kernel(unsigned *__restrict__ p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0u;
+}
+
 }  // namespace
 
 #define DISPATCH_T(dtype, ...)            \
@@ -688,6 +701,28 @@ int prep_scaled_bias(const float *b, const float *scale, float *out, int N, cuda
 int layerscale_grad_finalize(const float *G, const float *s, const float *W, const float *b, const float *gamma, float *dW,
                              float *db, float *dgamma, int N, int K, cudaStream_t st) {
   ls_finalize_kernel<<<ceil_div(N, 8), 256, 0, st>>>((float *)G, (float *)s, W, b, gamma, dW, db, dgamma, N, K);
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int device_copy(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if ((((uintptr_t)dst | (uintptr_t)src) & 15) != 0) {   // unaligned: leave it to the runtime
+    LEOD_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+  const int64_t n16 = (int64_t)(bytes / 16);
+  const int ntail = (int)(bytes % 16);
+  copy_u4_kernel<<<blocks_for(std::max<int64_t>(n16, ntail), 256), 256, 0, st>>>((const uint4 *)src, (uint4 *)dst, n16,
+                                                                                (const unsigned char *)src + n16 * 16,
+                                                                                (unsigned char *)dst + n16 * 16, ntail);
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int device_zero_u32(unsigned *p, int64_t n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  zero_u32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, n);
   LEOD_LAUNCH_CHECK();
   return 0;
 }

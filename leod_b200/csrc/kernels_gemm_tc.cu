@@ -1447,7 +1447,7 @@ int lstm_seq_fwd_tc(void *gates, const void *Wh, int ldw, const void *h0, const 
     LEOD_CUDA(cudaFuncSetAttribute(lstm_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     attr_set = true;
   }
-  LEOD_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (size_t)a.tiles_m * L, st));
+  LEOD_TRY(device_zero_u32(flags, (int64_t)a.tiles_m * L, st));
   const int grid = a.split ? a.tiles_m * a.npass : std::min(a.tiles_m, num_sms());
   lstm_seq_fwd_kernel<<<grid, LS_THREADS, smem, st>>>(mH, mH0, mW, a);
   LEOD_LAUNCH_CHECK();
@@ -1487,7 +1487,7 @@ int lstm_seq_bwd_tc(const void *gates, const void *c_all, const void *c0, const 
     LEOD_CUDA(cudaFuncSetAttribute(lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
     attr_set = true;
   }
-  LEOD_CUDA(cudaMemsetAsync(flags, 0, sizeof(unsigned) * (size_t)a.tiles_m * L, st));
+  LEOD_TRY(device_zero_u32(flags, (int64_t)a.tiles_m * L, st));
   const int grid = a.split ? a.tiles_m * a.npass : std::min(a.tiles_m, num_sms());
   lstm_seq_bwd_kernel<<<grid, LS_THREADS, smem, st>>>(mG, mW, a);
   LEOD_LAUNCH_CHECK();

@@ -61,13 +61,23 @@ class _GraphedDetect:
         self.pg = [(p, g) for p, g in zip(self.params, grads[nf:]) if g is not None]
 
     def replay(self, feats, labels):
-        for s, f in zip(self.s_feats, feats):
-            s.data.copy_(f)
-        self.s_labels.copy_(labels)
+        # Multi-tensor copy KERNELS, not Tensor.copy_/clone: dense same-layout device copies go to a copy engine, where
+        # they would queue behind the bulk host->device upload of the next step's input batch.
+        th._foreach_copy_([s.data for s in self.s_feats], [f.detach() for f in feats])
+        th._foreach_copy_([self.s_labels], [labels.detach()])
         self.graph.replay()
         scal = [k for k, v in self.s_losses.items() if th.is_tensor(v)]
         self.keys = scal
-        return (self.s_losses['loss'].clone(), self.s_preds.clone()) + tuple(self.s_losses[k].clone() for k in scal if k != 'loss')
+        src = [self.s_losses['loss'], self.s_preds] + [self.s_losses[k] for k in scal if k != 'loss']
+        out = [th.empty_like(t) for t in src]
+        by_dtype = {}
+        for o, t in zip(out, src):
+            by_dtype.setdefault(t.dtype, ([], []))
+            by_dtype[t.dtype][0].append(o)
+            by_dtype[t.dtype][1].append(t)
+        for dst, srcs in by_dtype.values():
+            th._foreach_copy_(dst, srcs)
+        return tuple(out)
 
     def grads(self, g_loss):
         ps = [p for p, _ in self.pg]
