@@ -291,6 +291,94 @@ def gen_optim():
     print('optim_cases.npz')
 
 
+def synth_track_sequence(seed, n_frames, hw, n_obj, ncls, miss_p=0.2, fp_rate=0.6, gt_frames=(), drop_frames=()):
+    """Synthetic per-frame detections of a sequence, as ObjectLabels rows (t, x, y, w, h, cls, cls_conf, obj_conf),
+    corner format: objects on straight tracks (some leaving the image), random misses, short-lived false positives."""
+    rng = np.random.default_rng(seed)
+    H, W = hw
+    objs = []
+    for _ in range(n_obj):
+        w, h = rng.uniform(15, 70), rng.uniform(12, 50)
+        objs.append(dict(x=rng.uniform(-20, W), y=rng.uniform(0, H - h), w=w, h=h, vx=rng.uniform(-6, 6), vy=rng.uniform(-2, 2),
+                         cls=int(rng.integers(0, ncls)), t0=int(rng.integers(0, n_frames // 2)), t1=int(rng.integers(n_frames // 2, n_frames + 1))))
+    frames, idx = [], []
+    for f in range(n_frames):
+        if f in drop_frames:
+            continue
+        rows = []
+        gt = f in gt_frames
+        for o in objs:
+            if not (o['t0'] <= f < o['t1']) or (rng.random() < miss_p and not gt):
+                continue
+            x = o['x'] + o['vx'] * (f - o['t0']) + rng.normal(0, 0.7)
+            y = o['y'] + o['vy'] * (f - o['t0']) + rng.normal(0, 0.7)
+            x1, y1 = np.clip(x, 0, W - 1), np.clip(y, 0, H - 1)
+            x2, y2 = np.clip(x + o['w'], 0, W - 1), np.clip(y + o['h'], 0, H - 1)
+            if x2 - x1 < 5 or y2 - y1 < 5:
+                continue
+            rows.append([1.0 if gt else 0.0, x1, y1, x2 - x1, y2 - y1, o['cls'], 1.0 if gt else rng.uniform(0.4, 1), 1.0 if gt else rng.uniform(0.4, 1)])
+        if not gt:
+            for _ in range(rng.poisson(fp_rate)):
+                w, h = rng.uniform(8, 40), rng.uniform(8, 40)
+                rows.append([0.0, rng.uniform(0, W - w - 1), rng.uniform(0, H - h - 1), w, h, int(rng.integers(0, ncls)), rng.uniform(0.3, 0.7), rng.uniform(0.3, 0.7)])
+        if rows:
+            frames.append(np.asarray(rows, np.float32))
+            idx.append(f)
+    return frames, idx
+
+
+def gen_tracking():
+    """modules/pseudo_labeler.py:201-333 (EventSeqData._track / _track_filter) with modules/tracking/linear.py run on
+    synthetic sequences: which boxes become `ignore` (class 1024), which boxes are in-painted, the final label lists."""
+    from modules.pseudo_labeler import EventSeqData
+    from data.genx_utils.labels import ObjectLabels
+    cases = [dict(seed=1, n_frames=40, hw=(240, 304), n_obj=4, ncls=2, gt_frames=(), drop_frames=()),
+             dict(seed=2, n_frames=60, hw=(240, 304), n_obj=7, ncls=2, gt_frames=(20, 40), drop_frames=(5, 6, 7, 30)),
+             dict(seed=3, n_frames=50, hw=(360, 640), n_obj=10, ncls=3, miss_p=0.35, fp_rate=1.5, gt_frames=(25,), drop_frames=()),
+             dict(seed=4, n_frames=12, hw=(240, 304), n_obj=2, ncls=2, miss_p=0.0, fp_rate=0.0),
+             dict(seed=5, n_frames=30, hw=(240, 304), n_obj=3, ncls=2, miss_p=0.5, fp_rate=0.2)]
+    out = {'n': np.int64(len(cases))}
+    for ci, c in enumerate(cases):
+        hw = c['hw']
+        frames, idx = synth_track_sequence(**c)
+        out[f'{ci}/hw'] = np.array(hw, np.int64)
+        out[f'{ci}/frame_idx'] = np.array(idx, np.int64)
+        out[f'{ci}/counts'] = np.array([len(f) for f in frames], np.int64)
+        out[f'{ci}/rows'] = np.concatenate(frames, 0)
+        for inpaint in (False, True):
+            labels = [ObjectLabels(torch.from_numpy(f.copy()), hw) for f in frames]
+            remove_idx, inpainted = EventSeqData._track(labels, list(idx), min_track_len=6, inpaint=inpaint)
+            out[f'{ci}/remove_idx_inpaint{int(inpaint)}'] = np.array(sorted(remove_idx), np.int64)
+            if inpaint:
+                keys = sorted(inpainted.keys())
+                out[f'{ci}/inpaint_frames'] = np.array(keys, np.int64)
+                out[f'{ci}/inpaint_counts'] = np.array([len(inpainted[k]) for k in keys], np.int64)
+                out[f'{ci}/inpaint_rows'] = np.concatenate([inpainted[k] for k in keys], 0) if keys else np.zeros((0, 8), np.float32)
+        # the whole post-processing: forward or backward tracking, ignore labels, in-painting
+        for method in ('forward', 'forward or backward'):
+            seq = EventSeqData.__new__(EventSeqData)
+            seq.filter_config = DictConfig(dict(min_track_len=6, track_method=method, inpaint=True, ignore_label=1024))
+            seq.labels = [ObjectLabels(torch.from_numpy(f.copy()), hw) for f in frames]
+            seq.frame_idx = list(idx)
+            seq._track_filter()
+            tag = 'fb' if 'backward' in method else 'f'
+            out[f'{ci}/final_{tag}_frame_idx'] = np.array(seq.frame_idx, np.int64)
+            out[f'{ci}/final_{tag}_counts'] = np.array([len(l) for l in seq.labels], np.int64)
+            rows = []
+            for l in seq.labels:
+                l.numpy_()
+                rows.append(np.asarray(l.object_labels, np.float32))
+            out[f'{ci}/final_{tag}_rows'] = np.concatenate(rows, 0)
+            if tag == 'fb':    # the on-disk records (pseudo_labeler.py:179-199 _summarize, labels.py:12-16 BBOX_DTYPE)
+                packed, lbl_idx, repr_idx = seq._summarize()
+                out[f'{ci}/packed_bytes'] = np.frombuffer(packed.tobytes(), np.uint8)
+                out[f'{ci}/objframe_idx_2_label_idx'] = lbl_idx
+                out[f'{ci}/objframe_idx_2_repr_idx'] = repr_idx
+        print('tracking case', ci, 'boxes', int(out[f'{ci}/counts'].sum()), 'removed', len(out[f'{ci}/remove_idx_inpaint1']),
+              'inpainted', int(out[f'{ci}/inpaint_counts'].sum()))
+    np.savez_compressed(os.path.join(HERE, 'tracking_cases.npz'), **out)
+
+
 def gen_fullsize():
     """Full-size runs of the REFERENCE itself (BASELINE configs[0]: RVT-tiny, 10 input channels, 1 x 240 x 304, one
     frame; and the configs[1] model RVT-small at batch 1, two frames) with name-seeded weights (tests/helpers.py:
@@ -333,4 +421,5 @@ if __name__ == '__main__':
     gen_pred2label()
     gen_binning()
     gen_optim()
+    gen_tracking()
     gen_fullsize()

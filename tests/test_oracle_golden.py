@@ -151,3 +151,50 @@ def test_full_size_oracle_matches_reference_run(tag):
     dets = opp.postprocess(z[f'{tag}/preds'], ocfg.num_classes, 0.001, 0.45)
     for b in range(B):   # anchors over the zero-padded rows produce exactly equal scores: compare order-independently there
         np.testing.assert_allclose(canon_rows(dets[b]), canon_rows(z[f'{tag}/det{b}']), rtol=0, atol=1e-5)
+
+
+def _split(rows, counts):
+    out, o = [], 0
+    for n in counts:
+        out.append(rows[o:o + int(n)])
+        o += int(n)
+    return out
+
+
+def test_tracking_filter_matches_reference():
+    """oracle/tracking.py against EventSeqData._track / _track_filter + LinearTracker of the reference run on synthetic
+    sequences (tests/golden/make_golden.py: gen_tracking): ignored boxes, in-painted boxes, final per-frame labels."""
+    from oracle import tracking as otr
+    z = np.load(os.path.join(GOLDEN, 'tracking_cases.npz'))
+    for ci in range(int(z['n'])):
+        hw = tuple(int(v) for v in z[f'{ci}/hw'])
+        frame_idx = [int(v) for v in z[f'{ci}/frame_idx']]
+        frames = _split(z[f'{ci}/rows'], z[f'{ci}/counts'])
+        for inpaint in (False, True):
+            remove, holes = otr.track(frames, frame_idx, hw, min_track_len=6, inpaint=inpaint)
+            np.testing.assert_array_equal(np.array(sorted(remove), np.int64), z[f'{ci}/remove_idx_inpaint{int(inpaint)}'])
+            if inpaint:
+                keys = sorted(holes.keys())
+                np.testing.assert_array_equal(np.array(keys, np.int64), z[f'{ci}/inpaint_frames'])
+                np.testing.assert_array_equal(np.array([len(holes[k]) for k in keys], np.int64), z[f'{ci}/inpaint_counts'])
+                got = np.concatenate([holes[k] for k in keys], 0) if keys else np.zeros((0, 8), np.float32)
+                np.testing.assert_array_equal(got, z[f'{ci}/inpaint_rows'])
+        for tag, method in (('f', 'forward'), ('fb', 'forward or backward')):
+            fidx, rows = otr.track_filter(frames, frame_idx, hw, min_track_len=6, method=method, inpaint=True, ignore_label=1024)
+            np.testing.assert_array_equal(np.array(fidx, np.int64), z[f'{ci}/final_{tag}_frame_idx'])
+            np.testing.assert_array_equal(np.array([len(r) for r in rows], np.int64), z[f'{ci}/final_{tag}_counts'])
+            np.testing.assert_array_equal(np.concatenate(rows, 0), z[f'{ci}/final_{tag}_rows'])
+
+
+def test_label_records_match_reference_bytes():
+    """oracle/labels_io.py: the 40-byte BBOX_DTYPE records and the two index arrays the reference writes for a sequence
+    (EventSeqData._summarize), byte for byte."""
+    from oracle import labels_io
+    z = np.load(os.path.join(GOLDEN, 'tracking_cases.npz'))
+    for ci in range(int(z['n'])):
+        frames = _split(z[f'{ci}/final_fb_rows'], z[f'{ci}/final_fb_counts'])
+        recs, lbl_idx, repr_idx = labels_io.summarize(z[f'{ci}/final_fb_frame_idx'], frames)
+        assert recs.dtype.names == labels_io.BBOX_DTYPE.names and recs.dtype.itemsize in (36, 40)   # see labels_io.summarize
+        np.testing.assert_array_equal(np.frombuffer(recs.tobytes(), np.uint8), z[f'{ci}/packed_bytes'])
+        np.testing.assert_array_equal(lbl_idx, z[f'{ci}/objframe_idx_2_label_idx'])
+        np.testing.assert_array_equal(repr_idx, z[f'{ci}/objframe_idx_2_repr_idx'])
