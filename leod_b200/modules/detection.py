@@ -177,8 +177,9 @@ class Module(_Base):
         if sched is None or not sched.get('use', False):
             return opt
         total = sched.total_steps if hasattr(sched, 'total_steps') else tc.max_steps
+        # the reference interprets its final_div_factor as max_lr / final_lr (modules/detection.py:499-501)
         s = torch.optim.lr_scheduler.OneCycleLR(optimizer=opt, max_lr=tc.learning_rate, div_factor=sched.div_factor,
-                                                final_div_factor=sched.final_div_factor, total_steps=total,
+                                                final_div_factor=sched.final_div_factor / sched.div_factor, total_steps=total,
                                                 pct_start=sched.pct_start, cycle_momentum=False, anneal_strategy='linear')
         return {'optimizer': opt, 'lr_scheduler': {'scheduler': s, 'interval': 'step', 'frequency': 1, 'strict': True}}
 
@@ -188,6 +189,22 @@ class Module(_Base):
         if 'state_dict' in ckpt:
             ckpt = ckpt['state_dict']
         self.load_state_dict(ckpt, strict=strict)
+
+
+def one_cycle_lr(step: int, max_lr: float, total_steps: int, pct_start: float = 0.005, div_factor: float = 20.0,
+                 final_div_factor: float = 10000.0) -> float:
+    """Learning rate of optimizer step `step` (0-based) under the reference's schedule (modules/detection.py:495-510):
+    torch OneCycleLR, two linear phases, no momentum cycling, with the reference's reading of `final_div_factor` as
+    max_lr / final_lr.  Closed form for `FlatOptimizer.step(lr=...)`, which has no param_groups for a torch scheduler."""
+    initial = max_lr / div_factor
+    final = initial / (final_div_factor / div_factor)
+    up_end = float(pct_start * total_steps) - 1
+    down_end = total_steps - 1
+    if step <= up_end:
+        pct = step / up_end if up_end > 0 else 1.0
+        return (max_lr - initial) * pct + initial
+    pct = (step - up_end) / (down_end - up_end)
+    return (final - max_lr) * pct + max_lr
 
 
 class FlatOptimizer:

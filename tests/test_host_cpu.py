@@ -180,3 +180,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'event-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']
+
+
+@pytest.mark.parametrize('total,pct,lr', [(1000, 0.005, 2e-4), (400, 0.1, 3.46e-4), (50, 0.3, 1e-3)])
+def test_one_cycle_lr_matches_torch_scheduler(total, pct, lr):
+    """The closed-form schedule used with FlatOptimizer equals torch's OneCycleLR configured as the reference does
+    (modules/detection.py:495-510: linear anneal, final_div_factor / div_factor, no momentum cycling)."""
+    from leod_b200.modules.detection import one_cycle_lr
+    div, final_div = 20.0, 10000.0
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=lr)
+    sch = torch.optim.lr_scheduler.OneCycleLR(optimizer=opt, max_lr=lr, div_factor=div, final_div_factor=final_div / div, total_steps=total,
+                                              pct_start=pct, cycle_momentum=False, anneal_strategy='linear')
+    for step in range(total):
+        assert abs(opt.param_groups[0]['lr'] - one_cycle_lr(step, lr, total, pct, div, final_div)) < 1e-12 + 1e-9 * lr, step
+        opt.step()
+        if step + 1 < total:
+            sch.step()
