@@ -24,6 +24,13 @@ class DataType(Enum):
     AUGM_STATE = auto()
 
 
+class DatasetSamplingMode(Enum):
+    """data/utils/types.py:46-49 (the reference derives from StrEnum; values are the same strings)."""
+    RANDOM = 'random'
+    STREAM = 'stream'
+    MIXED = 'mixed'
+
+
 def dget(data: dict, key: DataType, default=None):
     """Look a DataType up by NAME so dicts keyed by the reference's own enum class work too."""
     if key in data:

@@ -15,7 +15,7 @@ import torch.nn as nn
 from leod_b200.data.utils.types import DataType, dget
 from leod_b200.models.detection.yolox.utils.boxes import postprocess
 from leod_b200.models.detection.yolox_extension.models.detector import YoloXDetector
-from .utils.detection import DATA_KEY, WORKER_ID_KEY, BackboneFeatureSelector, Mode, RNNStates, mode_2_string
+from .utils.detection import DATA_KEY, WORKER_ID_KEY, BackboneFeatureSelector, Mode, RNNStates, merge_mixed_batches, mode_2_string
 from .utils.ssod import fused_adamw_ema
 
 try:  # pragma: no cover - not installed in the build image
@@ -73,6 +73,7 @@ class Module(_Base):
 
     # ------------------------------------------------------------------ train
     def training_step(self, batch: Any, batch_idx: int = 0, log: bool = False):
+        batch = merge_mixed_batches(batch)      # {RANDOM: ..., STREAM: ...} of the mixed sampler -> one batch (:152)
         data = self.get_data_from_batch(batch)
         worker_id = batch[WORKER_ID_KEY]
         mode = Mode.TRAIN

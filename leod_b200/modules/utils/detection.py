@@ -114,3 +114,50 @@ class SeqLens:
             assert len(indices_or_bool_tensor) > 0
             idx = indices_or_bool_tensor.cpu() if th.is_tensor(indices_or_bool_tensor) else indices_or_bool_tensor
             self.lens[worker_id][idx] = 0
+
+
+def _by_name(d: dict, name: str):
+    for k, v in d.items():
+        if k == name or getattr(k, 'name', None) == name or getattr(k, 'value', None) == name.lower():
+            return v
+    raise KeyError(name)
+
+
+def mixed_collate_fn(x1, x2):
+    """Concatenate the stream half and the random-access half of a mixed batch along the batch axis
+    (modules/utils/detection.py:195-223): tensors, per-timestep lists, label containers, string lists, nested dicts."""
+    if isinstance(x1, th.Tensor):
+        assert isinstance(x2, th.Tensor)
+        return th.cat((x1, x2))
+    if hasattr(x1, 'sparse_object_labels_batch'):          # SparselyBatchedObjectLabels (ours or the reference's)
+        return x1 + x2
+    if isinstance(x1, list):
+        assert isinstance(x2, list) and len(x1) == len(x2)
+        if len(x1) and isinstance(x1[0], str):
+            return x1 + x2
+        return [mixed_collate_fn(a, b) for a, b in zip(x1, x2)]
+    if isinstance(x1, dict):
+        assert isinstance(x2, dict)
+        out = {}
+        for k in x1:
+            if isinstance(x1[k], dict):
+                out[k] = mixed_collate_fn(x1[k], x2[k])
+            elif isinstance(x1[k], list):
+                out[k] = x1[k] + x2[k]
+            else:
+                raise NotImplementedError(f'{type(x1[k])=}, {type(x2[k])=}')
+        return out
+    raise NotImplementedError(f'{type(x1)=}, {type(x2)=}')
+
+
+def merge_mixed_batches(batch: dict):
+    """modules/utils/detection.py:226-240: {RANDOM: batch, STREAM: batch} -> one batch, stream rows first; the worker id
+    (key of the recurrent-state store) is the streaming loader's."""
+    if DATA_KEY in batch:
+        return batch
+    rnd_data = _by_name(batch, 'RANDOM')[DATA_KEY]
+    stream_batch = _by_name(batch, 'STREAM')
+    stream_data = stream_batch[DATA_KEY]
+    assert rnd_data.keys() == stream_data.keys(), f'{rnd_data.keys()=}, {stream_data.keys()=}'
+    return {WORKER_ID_KEY: stream_batch[WORKER_ID_KEY],
+            DATA_KEY: {k: mixed_collate_fn(stream_data[k], rnd_data[k]) for k in rnd_data.keys()}}

@@ -197,3 +197,29 @@ def test_one_cycle_lr_matches_torch_scheduler(total, pct, lr):
         opt.step()
         if step + 1 < total:
             sch.step()
+
+
+def test_merge_mixed_batches_contract():
+    """modules/utils/detection.py:226-240: stream rows first, random-access rows after; worker id of the stream loader;
+    tensors / per-timestep lists / label containers / paths all concatenated along the batch axis."""
+    from leod_b200.data.labels import ObjectLabels, SparselyBatchedObjectLabels
+    from leod_b200.data.utils.types import DatasetSamplingMode, DataType
+    from leod_b200.modules.utils.detection import merge_mixed_batches
+    L = 3
+
+    def half(B, base, wid):
+        lab = [SparselyBatchedObjectLabels([ObjectLabels(torch.full((1, 8), float(base + b)), (240, 304)) if t == L - 1 else None
+                                            for b in range(B)]) for t in range(L)]
+        return {'worker_id': wid, 'data': {DataType.EV_REPR: [torch.full((B, 2, 4, 4), float(base + t)) for t in range(L)],
+                                           DataType.OBJLABELS_SEQ: lab, DataType.IS_FIRST_SAMPLE: torch.tensor([base == 100] * B),
+                                           DataType.PATH: [f'p{base + b}' for b in range(B)]}}
+    merged = merge_mixed_batches({DatasetSamplingMode.RANDOM: half(2, 100, 7), DatasetSamplingMode.STREAM: half(2, 0, 4)})
+    assert merged['worker_id'] == 4
+    d = merged['data']
+    assert [tuple(x.shape) for x in d[DataType.EV_REPR]] == [(4, 2, 4, 4)] * L
+    assert d[DataType.EV_REPR][1][:, 0, 0, 0].tolist() == [1.0, 1.0, 101.0, 101.0]
+    assert d[DataType.IS_FIRST_SAMPLE].tolist() == [False, False, True, True]
+    assert d[DataType.PATH] == ['p0', 'p1', 'p100', 'p101']
+    last = d[DataType.OBJLABELS_SEQ][L - 1]
+    assert len(last) == 4 and [float(last[b].object_labels[0, 0]) for b in range(4)] == [0.0, 1.0, 100.0, 101.0]
+    assert merge_mixed_batches(merged) is merged          # already merged batches pass through
