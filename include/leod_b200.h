@@ -31,7 +31,7 @@ int leod_abi_version(void);
 unsigned long long leod_launch_count(void);
 /* Per-kernel-class timing with CUDA events on the launching stream (measurement aid for bench.py;
  * off by default).  Kinds: 0 gemm_nt, 1 gemm_tn, 2 attention fwd, 3 attention bwd, 4 layernorm,
- * 5 lstm gates, 6 patch gather/scatter, 7 other.  collect(): out[kind*4 + {0,1,2,3}] = launches,
+ * 5 lstm gates, 6 patch gather/scatter, 7 other, 8 neck/head convolution GEMMs.  collect(): out[kind*4 + {0,1,2,3}] = launches,
  * total ms, algorithmic FLOPs, algorithmic bytes since the last collect. */
 int leod_profile_enable(int on);
 /* Debug: route bf16 attention through the SIMT kernel instead of the tensor-core one. */
@@ -157,6 +157,77 @@ int leod_layernorm_bwd(int dtype, const void *x, const float *w, const void *dy,
 int leod_lstm_gates_fwd(int dtype, void *gates, const void *c_prev, void *h_out, void *c_out, int M, int C, void *stream);
 int leod_lstm_gates_bwd(int dtype, const void *gates, const void *c_prev, const void *c_out, const void *dh, const void *dh2,
                         const void *dc, void *dgates, void *dc_prev, int M, int C, void *stream);
+
+/* ------------------------------------------------------------------ PAFPN neck + YOLOX head + SimOTA loss
+ * Replaces models/detection/yolox_extension/models/yolo_pafpn.py:18-140 (YOLOPAFPN), models/detection/yolox/models/
+ * network_blocks.py:29-142 (BaseConv / Bottleneck / CSPLayer), models/detection/yolox/models/yolo_head.py:21-332 (YOLOXHead
+ * forward + decode) and :382-1148 (get_losses / get_assignments / SimOTA, plain and ignore-label variants), i.e. everything
+ * behind YoloXDetector.forward_detect (models/detection/yolox_extension/models/detector.py:55-77). */
+typedef struct leod_detect leod_detect_t;
+
+typedef struct {
+  int32_t in_channels[3];   /* backbone.get_stage_dims(fpn.in_stages), stride 8 / 16 / 32 level first to last */
+  int32_t strides[3];       /* backbone.get_strides(fpn.in_stages): 8, 16, 32                                */
+  int32_t num_classes;      /* head.num_classes (1..3)                                                        */
+  int32_t n_bottleneck;     /* round(3 * fpn.depth): bottlenecks per CSPLayer                                 */
+  int32_t in_h, in_w;       /* backbone.in_res_hw (level l is in_h/strides[l] x in_w/strides[l])              */
+  int32_t dtype;            /* LEOD_F32 or LEOD_BF16: activation storage / GEMM operand type                  */
+  float bn_eps, bn_momentum;/* nn.BatchNorm2d defaults 1e-5, 0.1 (network_blocks.py:46)                       */
+  float ignore_label;       /* head.ignore_label (1024)                                                       */
+  int32_t n_ignore_thresh;  /* len(head.ignore_bbox_thresh) or 0                                              */
+  float ignore_thresh[8];
+  float reg_weight, obj_weight, cls_weight;   /* 5, 1, 1 (yolo_head.py:67-69)                                 */
+} leod_detect_cfg;
+
+int leod_detect_create(const leod_detect_cfg *cfg, leod_detect_t **out);
+/* Without any device allocation: only the *_info / *_count queries and _destroy are valid on the result. */
+int leod_detect_layout_only(const leod_detect_cfg *cfg, leod_detect_t **out);
+void leod_detect_destroy(leod_detect_t *h);
+/* Flat buffers.  Parameters (fp32): entry names are the reference state_dict keys ("fpn.lateral_conv0.conv.weight",
+ * "yolox_head.cls_preds.0.bias", ...).  Buffers (fp32): BatchNorm running_mean / running_var.  Counters (int64):
+ * num_batches_tracked.  Each returns the number of entries when i < 0. */
+int leod_detect_param_info(const leod_detect_t *h, int i, char *name, size_t name_cap, int64_t *offset, int32_t *ndim, int64_t shape[4]);
+int leod_detect_buffer_info(const leod_detect_t *h, int i, char *name, size_t name_cap, int64_t *offset, int32_t *ndim, int64_t shape[4]);
+int leod_detect_counter_info(const leod_detect_t *h, int i, char *name, size_t name_cap, int64_t *offset);
+int64_t leod_detect_param_count(const leod_detect_t *h);
+int64_t leod_detect_buffer_count(const leod_detect_t *h);
+int64_t leod_detect_counter_count(const leod_detect_t *h);
+int leod_detect_num_anchors(const leod_detect_t *h);
+/* grads may be NULL for inference-only handles; counters may be NULL. */
+int leod_detect_bind(leod_detect_t *h, float *params_dev, float *grads_dev, float *buffers_dev, int64_t *counters_dev);
+/* Re-derive the operand-typed weight copies; call after every parameter update and before the next forward. */
+int leod_detect_prepare(leod_detect_t *h, void *stream);
+/* Pre-size the activation arena for up to B images (call outside CUDA-graph capture). */
+int leod_detect_reserve(leod_detect_t *h, int B);
+/* SyncBatchNorm (train.py:247): fn(ctx, buf, n, stream) must sum the n doubles at device pointer buf over all ranks, in place,
+ * ordered on `stream`.  It is called once per dependency level of the network (forward: sums / sums of squares / counts,
+ * backward: the two BatchNorm gradient sums), not once per layer.  NULL = single process. */
+typedef int (*leod_allreduce_fn)(void *ctx, double *buf, int64_t n, void *stream);
+int leod_detect_set_allreduce(leod_detect_t *h, leod_allreduce_fn fn, void *ctx);
+
+/* yolo_pafpn.py:109-140 + yolo_head.py:195-287, 310-332.
+ *  feats[l] : device, dense channels-last [B, h_l, w_l, in_channels[l]] in the handle's dtype
+ *  training : != 0 -> BatchNorm batch statistics (+ running-statistics update) and activations kept for the backward
+ *  preds    : device fp32 [B, A, 5 + num_classes] = decoded (cx, cy, w, h), sigmoid(obj), sigmoid(cls); A = leod_detect_num_anchors */
+int leod_fpn_head_fwd(leod_detect_t *h, const void *const feats[3], int B, int training, float *preds, void *stream);
+/* yolo_head.py:403-597 / 776-972 on the outputs of the preceding training-mode leod_fpn_head_fwd.
+ *  labels     : device fp32 [B, nmax, 7] rows (cls, cx, cy, w, h, obj_conf, cls_conf), all-zero rows = padding
+ *  losses_out : device fp32 [6] = loss, iou_loss, conf_loss, cls_loss, l1_loss (always 0), num_fg / num_gts */
+int leod_simota_loss_fwd(leod_detect_t *h, const float *labels, int nmax, float *losses_out, void *stream);
+/* Diagnostics: the assignment of the last leod_simota_loss_fwd.  assign_out: device int32 [B, A] label row per anchor (-1 =
+ * background, yolo_head.py:768-774 matched_gt_inds); miou_out (NULL allowed): device fp32 [B, A] pred_ious_this_matching. */
+int leod_simota_assignment(leod_detect_t *h, int32_t *assign_out, float *miou_out, void *stream);
+/* d(gscale * loss)/d(raw head outputs); gscale: device fp32 scalar or NULL (= 1).  Result stays inside the handle. */
+int leod_simota_loss_bwd(leod_detect_t *h, const float *labels, int nmax, const float *gscale, void *stream);
+/* Raw (undecoded) head outputs / their gradients as dense device fp32 [B, A, 8] tensors (columns: reg x4, obj logit, class logits,
+ * zero padding; yolo_head.py:236 `output` before get_output_and_grid).  _get_raw: outputs of the last forward.  _get_raw_grad: the
+ * result of leod_simota_loss_bwd.  _set_raw_grad: replace it with the gradient of a caller-defined loss before leod_fpn_head_bwd. */
+int leod_detect_get_raw(leod_detect_t *h, float *out, void *stream);
+int leod_detect_get_raw_grad(leod_detect_t *h, float *out, void *stream);
+int leod_detect_set_raw_grad(leod_detect_t *h, const float *in, void *stream);
+/* Backward of the neck + head.  Parameter gradients are ACCUMULATED into the bound gradient buffer; dfeats[l] (same layout as
+ * feats[l], NULL entries allowed) are written.  Fails if another forward overwrote the activations since the training forward. */
+int leod_fpn_head_bwd(leod_detect_t *h, void *const dfeats[3], void *stream);
 
 /* ------------------------------------------------------------------ detection post-processing
  * Replaces models/detection/yolox/utils/boxes.py:32-86 (postprocess) including the

@@ -21,7 +21,18 @@ class BackboneCfg(Structure):
                 ('ln_eps', c_float)]
 
 
+class DetectCfg(Structure):
+    _fields_ = [('in_channels', c_int32 * 3), ('strides', c_int32 * 3), ('num_classes', c_int32), ('n_bottleneck', c_int32),
+                ('in_h', c_int32), ('in_w', c_int32), ('dtype', c_int32), ('bn_eps', c_float), ('bn_momentum', c_float),
+                ('ignore_label', c_float), ('n_ignore_thresh', c_int32), ('ignore_thresh', c_float * 8),
+                ('reg_weight', c_float), ('obj_weight', c_float), ('cls_weight', c_float)]
+
+
+# int fn(void *ctx, double *buf, int64_t n, void *stream): sum buf over the ranks (leod_detect_set_allreduce)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_int64, c_void_p)
+
 _VP4 = c_void_p * 4
+_VP3 = c_void_p * 3
 _lib = None
 
 
@@ -59,6 +70,28 @@ def _declare(lib):
         'leod_layernorm_bwd': (I, [I, VP, VP, VP, VP, VP, VP, VP, I, I, F, VP]),
         'leod_lstm_gates_fwd': (I, [I, VP, VP, VP, VP, I, I, VP]),
         'leod_lstm_gates_bwd': (I, [I, VP, VP, VP, VP, VP, VP, VP, VP, I, I, VP]),
+        'leod_detect_create': (I, [POINTER(DetectCfg), POINTER(VP)]),
+        'leod_detect_layout_only': (I, [POINTER(DetectCfg), POINTER(VP)]),
+        'leod_detect_destroy': (None, [VP]),
+        'leod_detect_param_info': (I, [VP, I, c_char_p, c_size_t, POINTER(c_int64), POINTER(c_int32), POINTER(c_int64 * 4)]),
+        'leod_detect_buffer_info': (I, [VP, I, c_char_p, c_size_t, POINTER(c_int64), POINTER(c_int32), POINTER(c_int64 * 4)]),
+        'leod_detect_counter_info': (I, [VP, I, c_char_p, c_size_t, POINTER(c_int64)]),
+        'leod_detect_param_count': (c_int64, [VP]),
+        'leod_detect_buffer_count': (c_int64, [VP]),
+        'leod_detect_counter_count': (c_int64, [VP]),
+        'leod_detect_num_anchors': (I, [VP]),
+        'leod_detect_bind': (I, [VP, VP, VP, VP, VP]),
+        'leod_detect_prepare': (I, [VP, VP]),
+        'leod_detect_reserve': (I, [VP, I]),
+        'leod_detect_set_allreduce': (I, [VP, ALLREDUCE_FN, VP]),
+        'leod_fpn_head_fwd': (I, [VP, _VP3, I, I, VP, VP]),
+        'leod_simota_loss_fwd': (I, [VP, VP, I, VP, VP]),
+        'leod_simota_loss_bwd': (I, [VP, VP, I, VP, VP]),
+        'leod_simota_assignment': (I, [VP, VP, VP, VP]),
+        'leod_detect_get_raw': (I, [VP, VP, VP]),
+        'leod_detect_get_raw_grad': (I, [VP, VP, VP]),
+        'leod_detect_set_raw_grad': (I, [VP, VP, VP]),
+        'leod_fpn_head_bwd': (I, [VP, _VP3, VP]),
         'leod_postprocess': (I, [VP, I, I, I, F, F, I, VP, VP, I, VP]),
         'leod_pred2label': (I, [VP, VP, I, I, I, POINTER(c_float), POINTER(c_float), I, I, VP, VP, VP]),
         'leod_tta_merge': (I, [VP, VP, I, I, F, F, I, VP, VP, VP]),
@@ -80,7 +113,11 @@ EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 
                     'leod_backbone_step_fwd', 'leod_backbone_step_bwd', 'leod_backbone_grads_finalize', 'leod_backbone_seq_arena_bytes',
                     'leod_backbone_seq_fwd', 'leod_backbone_seq_bwd', 'leod_gemm_nt',
                     'leod_gemm_tn', 'leod_attention_fwd', 'leod_attention_bwd', 'leod_layernorm_fwd', 'leod_layernorm_bwd',
-                    'leod_lstm_gates_fwd', 'leod_lstm_gates_bwd', 'leod_postprocess', 'leod_pred2label', 'leod_tta_merge',
+                    'leod_lstm_gates_fwd', 'leod_lstm_gates_bwd', 'leod_detect_create', 'leod_detect_layout_only', 'leod_detect_destroy',
+                    'leod_detect_param_info', 'leod_detect_buffer_info', 'leod_detect_counter_info', 'leod_detect_param_count',
+                    'leod_detect_buffer_count', 'leod_detect_counter_count', 'leod_detect_num_anchors', 'leod_detect_bind',
+                    'leod_detect_prepare', 'leod_detect_reserve', 'leod_detect_set_allreduce', 'leod_fpn_head_fwd',
+                    'leod_simota_loss_fwd', 'leod_simota_loss_bwd', 'leod_simota_assignment', 'leod_detect_get_raw', 'leod_detect_get_raw_grad', 'leod_detect_set_raw_grad', 'leod_fpn_head_bwd', 'leod_postprocess', 'leod_pred2label', 'leod_tta_merge',
                     'leod_voxel_bin', 'leod_adamw_ema']
 
 
@@ -120,7 +157,19 @@ def vp4(tensors):
     return arr
 
 
-PROF_KINDS = ['gemm_nt', 'gemm_tn', 'attention_fwd', 'attention_bwd', 'layernorm', 'lstm_gates', 'patch', 'other']
+PROF_KINDS = ['gemm_nt', 'gemm_tn', 'attention_fwd', 'attention_bwd', 'layernorm', 'lstm_gates', 'patch', 'other', 'conv']
+
+
+class _DevArray:
+    """CUDA array interface over a raw device pointer (lets torch wrap library-owned memory without a copy)."""
+
+    def __init__(self, ptr_, n, typestr):
+        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': typestr, 'data': (int(ptr_), False), 'version': 2}
+
+
+def tensor_from_ptr(ptr_, n, dtype, device):
+    typestr = {torch.float64: '<f8', torch.float32: '<f4', torch.int32: '<i4'}[dtype]
+    return torch.as_tensor(_DevArray(ptr_, n, typestr), device=device)
 
 
 def profile_collect():

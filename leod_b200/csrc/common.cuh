@@ -36,7 +36,7 @@ extern unsigned long long g_leod_launches;  // kernels launched by this library 
   } while (0)
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline pass).
-enum ProfKind { PK_GEMM_NT = 0, PK_GEMM_TN, PK_ATTN_FWD, PK_ATTN_BWD, PK_LAYERNORM, PK_LSTM, PK_PATCH, PK_OTHER, PK_COUNT };
+enum ProfKind { PK_GEMM_NT = 0, PK_GEMM_TN, PK_ATTN_FWD, PK_ATTN_BWD, PK_LAYERNORM, PK_LSTM, PK_PATCH, PK_OTHER, PK_CONV, PK_COUNT };
 struct ProfScope {
   int slot;
   cudaStream_t st;
@@ -86,6 +86,15 @@ static inline size_t dtype_size(int dt) { return dt == LEOD_BF16 ? 2 : (dt == LE
 // epilogue modes of the NT GEMM (see leod_b200.h)
 enum { EPI_NONE = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_GELU_BWD = 3 };
 
+// Implicit-GEMM taps over a zero-bordered ("padded flat") channels-last matrix: a k x k stride-1 convolution is the sum
+// over taps of A[row + off[tap], 0..cin) * B[n, tap*cinp .. tap*cinp + cin)^T (kernels_conv.cu explains the layout).
+struct ConvTaps {
+  int n = 0;      // taps (0 / 1 = plain GEMM)
+  int cin = 0;    // A columns per tap
+  int cinp = 0;   // B columns per tap (cin rounded up to a multiple of 64, zero filled)
+  int off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+};
+
 struct GemmNT {
   const void *A; int lda;
   const void *A2; int lda2; int K1;
@@ -96,16 +105,18 @@ struct GemmNT {
   int epi;
   const void *R; int ldr;
   void *aux; int ldaux;
+  ConvTaps taps;       // taps.n > 1: K = taps.n * taps.cinp, A has taps.cin columns (A2 unused)
+  int out_f32 = 0;     // C is fp32 whatever the operand type (EPI_NONE only)
 };
 
 // kernels_gemm_simt.cu
 int gemm_nt_simt(int dtype, const GemmNT &g, cudaStream_t st);
 int gemm_tn_simt(int dtype, const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N,
-                 int K, cudaStream_t st);
+                 int K, cudaStream_t st, const ConvTaps *taps = nullptr);
 // kernels_gemm_tc.cu
 int gemm_nt_tc(const GemmNT &g, cudaStream_t st);
 int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N, int K,
-               cudaStream_t st);
+               cudaStream_t st, const ConvTaps *taps = nullptr);
 int lstm_seq_fwd_tc(void *gates, const void *Wh, int ldw, const void *h0, const void *c0, void *h_all, void *c_all, unsigned *flags,
                     int M, int C, int L, cudaStream_t st);
 int lstm_seq_bwd_tc(const void *gates, const void *c_all, const void *c0, const void *dh, const void *dc_last, void *dgates, void *dc_ws,
@@ -145,3 +156,57 @@ int prep_weight(int dtype, const float *src, const float *scale, void *dst, int 
 int prep_scaled_bias(const float *b, const float *scale, float *out, int N, cudaStream_t st);
 int layerscale_grad_finalize(const float *G, const float *s, const float *W, const float *b, const float *gamma, float *dW,
                              float *db, float *dgamma, int N, int K, cudaStream_t st);
+
+// ------------------------------------------------------------------ neck / head building blocks (kernels_conv.cu)
+// "Padded flat" geometry of one pyramid level: (h+2)*(w+2) rows per image, zero border.
+struct PadGeom {
+  int B, h, w, w2, P;
+  int64_t R;   // B * P rows
+};
+PadGeom make_pad_geom(int B, int h, int w);
+// One BatchNorm parameter segment (the fused twin convolutions of a CSP layer / head tower have two).
+struct BnSeg {
+  const float *gamma = nullptr, *beta = nullptr;
+  float *rmean = nullptr, *rvar = nullptr;
+  long long *nbt = nullptr;
+  float *dgamma = nullptr, *dbeta = nullptr;
+};
+int pad_gather(int dtype, const void *src, void *dst, int ldd, const PadGeom &g, int C, cudaStream_t st);
+int pad_scatter(int dtype, const void *src, int lds, void *dst, const PadGeom &g, int C, cudaStream_t st);
+int upsample2x(int dtype, const void *src, int lds, const PadGeom &gs, void *dst, int ldd, const PadGeom &gd, int C, cudaStream_t st);
+int upsample2x_bwd(int dtype, const void *ddst, int ldd, const PadGeom &gd, void *dsrc, int lds, const PadGeom &gs, int C, int accumulate,
+                   cudaStream_t st);
+int im2col_pad_s2(int dtype, const void *src, int lds, const PadGeom &gs, void *col, int ldcol, const PadGeom &go, int cin, int cinp,
+                  cudaStream_t st);
+int col2im_pad_s2(int dtype, const void *dcol, int ldcol, const PadGeom &go, void *dsrc, int lds, const PadGeom &gs, int cin, int cinp,
+                  int accumulate, cudaStream_t st);
+int bn_stats(int dtype, const void *Y, int ldy, const PadGeom &g, int C, double *stats, cudaStream_t st);
+int bn_apply_silu(int dtype, const void *Y, int ldy, const PadGeom &g, int C, const double *stats, const BnSeg &s0, const BnSeg &s1, int cseg,
+                  void *Z, int ldz, float eps, float momentum, int training, cudaStream_t st);
+int bn_bwd_reduce(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, int C, const double *stats, const BnSeg &s0,
+                  const BnSeg &s1, int cseg, float eps, double *dstat, cudaStream_t st);
+int bn_bwd_apply(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, int C, const double *stats,
+                 const double *dstat_global, const double *dstat_local, const BnSeg &s0, const BnSeg &s1, int cseg, float eps, void *dY, int lddy,
+                 cudaStream_t st);
+int device_zero_bytes(void *p, size_t bytes, cudaStream_t st);
+
+// ------------------------------------------------------------------ head decode + SimOTA loss (kernels_simota.cu)
+struct HeadGeom {   // three pyramid levels, anchors level-major / row-major (yolo_head.py:297-299)
+  int B, A, C;
+  int h[3], w[3], a0[3], stride[3], P[3];
+};
+struct HeadPtrs { const float *raw[3]; };
+struct HeadGradPtrs { void *draw[3]; };
+struct SimotaCfg {
+  float ignore_label;
+  int n_thresh;
+  float thresh[8];
+  float reg_w, obj_w, cls_w;
+};
+int head_decode(const HeadPtrs &rp, const HeadGeom &g, const SimotaCfg &cfg, float *preds, float *tout, const float *labels, int nmax,
+                uint8_t *flags, int *match_cnt, int *match_gt, cudaStream_t st);
+int simota_loss_fwd(const HeadGeom &g, const SimotaCfg &cfg, const float *tout, const float *labels, int nmax, const uint8_t *flags,
+                    int *match_cnt, int *match_gt, int *assign, float *miou, double *sums, float *losses, cudaStream_t st);
+int simota_loss_bwd(int dtype, const HeadGeom &g, const SimotaCfg &cfg, const float *tout, const float *labels, int nmax, const uint8_t *flags,
+                    const int *assign, const float *miou, const double *sums, const float *gscale, const HeadGradPtrs &dp, cudaStream_t st);
+int raw_grad_copy(int dtype, const HeadGeom &g, float *flat, const HeadGradPtrs &dp, int set, cudaStream_t st);

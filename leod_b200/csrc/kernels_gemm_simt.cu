@@ -25,7 +25,10 @@ __device__ __forceinline__ void epilogue_store(const GemmNT &g, int m, int n, fl
     default:
       break;
   }
-  C[(size_t)m * g.ldc + n] = from_f<T>(v);
+  if (g.out_f32)
+    ((float *)g.C)[(size_t)m * g.ldc + n] = v;
+  else
+    C[(size_t)m * g.ldc + n] = from_f<T>(v);
 }
 
 template <typename T>
@@ -44,7 +47,13 @@ __global__ void __launch_bounds__(NT) gemm_nt_simt_kernel(const GemmNT g) {
       const int m = m0 + lr, n = n0 + lr;
       float av = 0.f, bv = 0.f;
       if (k < g.K) {
-        if (m < g.M) av = (k < g.K1) ? to_f<T>(A[(size_t)m * g.lda + k]) : to_f<T>(A2[(size_t)m * g.lda2 + (k - g.K1)]);
+        if (g.taps.n > 1) {   // implicit-GEMM taps: A row shifted per tap, rows outside [0, M) read as zero
+          const int tap = k / g.taps.cinp, kc = k - tap * g.taps.cinp;
+          const int r = m + g.taps.off[tap];
+          if (m < g.M && kc < g.taps.cin && r >= 0 && r < g.M) av = to_f<T>(A[(size_t)r * g.lda + kc]);
+        } else if (m < g.M) {
+          av = (k < g.K1) ? to_f<T>(A[(size_t)m * g.lda + k]) : to_f<T>(A2[(size_t)m * g.lda2 + (k - g.K1)]);
+        }
         if (n < g.N) bv = to_f<T>(B[(size_t)n * g.ldb + k]);
       }
       As[lk + j][lr] = av;
@@ -79,11 +88,14 @@ __global__ void __launch_bounds__(NT) gemm_nt_simt_kernel(const GemmNT g) {
 template <typename T>
 __global__ void __launch_bounds__(NT) gemm_tn_simt_kernel(const T *__restrict__ dY, int ldy, const T *__restrict__ X, int ldx,
                                                          float *__restrict__ dW, int ldw, float *__restrict__ dbias, int M,
-                                                         int N, int K, int rows_per_split) {
+                                                         int N, int K, int rows_per_split, const ConvTaps taps, int tiles_k) {
   __shared__ float Ys[BK][BN + PADW];
   __shared__ float Xs[BK][BN + PADW];
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
-  const int n0 = blockIdx.x * BN, k0 = blockIdx.y * BN;
+  const int tap = blockIdx.y / tiles_k;
+  const int n0 = blockIdx.x * BN, k0 = (blockIdx.y % tiles_k) * BN;
+  const int xoff = taps.n > 1 ? taps.off[tap] : 0;     // X row shift of this tap
+  dW += taps.n > 1 ? (size_t)tap * taps.cinp : 0;
   const int m_begin = blockIdx.z * rows_per_split;
   const int m_end = min(M, m_begin + rows_per_split);
   float acc[4][4] = {};
@@ -97,7 +109,8 @@ __global__ void __launch_bounds__(NT) gemm_tn_simt_kernel(const T *__restrict__ 
       float yv = 0.f, xv = 0.f;
       if (m < m_end) {
         if (n0 + lc + j < N) yv = to_f<T>(dY[(size_t)m * ldy + n0 + lc + j]);
-        if (k0 + lc + j < K) xv = to_f<T>(X[(size_t)m * ldx + k0 + lc + j]);
+        const int xr = m + xoff;
+        if (k0 + lc + j < K && xr >= 0 && xr < M) xv = to_f<T>(X[(size_t)xr * ldx + k0 + lc + j]);
       }
       Ys[lm][lc + j] = yv;
       Xs[lm][lc + j] = xv;
@@ -146,8 +159,11 @@ int gemm_nt_simt(int dtype, const GemmNT &g, cudaStream_t st) {
 }
 
 int gemm_tn_simt(int dtype, const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N,
-                 int K, cudaStream_t st) {
+                 int K, cudaStream_t st, const ConvTaps *taps) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  ConvTaps tp;
+  if (taps) tp = *taps;
+  const int ntap = tp.n > 1 ? tp.n : 1;
   const int tn = ceil_div(N, BN), tk = ceil_div(K, BN);
   int splits = ceil_div(148 * 4, tn * tk);
   const int max_splits = ceil_div(M, 4 * BK);
@@ -155,11 +171,11 @@ int gemm_tn_simt(int dtype, const void *dY, int ldy, const void *X, int ldx, flo
   if (splits < 1) splits = 1;
   int rows = (int)round_up(ceil_div(M, splits), BK);
   splits = ceil_div(M, rows);
-  dim3 grid(tn, tk, splits);
+  dim3 grid(tn, tk * ntap, splits);
   if (dtype == LEOD_F32)
-    gemm_tn_simt_kernel<float><<<grid, NT, 0, st>>>((const float *)dY, ldy, (const float *)X, ldx, dW, ldw, dbias, M, N, K, rows);
+    gemm_tn_simt_kernel<float><<<grid, NT, 0, st>>>((const float *)dY, ldy, (const float *)X, ldx, dW, ldw, dbias, M, N, K, rows, tp, tk);
   else
-    gemm_tn_simt_kernel<bf16><<<grid, NT, 0, st>>>((const bf16 *)dY, ldy, (const bf16 *)X, ldx, dW, ldw, dbias, M, N, K, rows);
+    gemm_tn_simt_kernel<bf16><<<grid, NT, 0, st>>>((const bf16 *)dY, ldy, (const bf16 *)X, ldx, dW, ldw, dbias, M, N, K, rows, tp, tk);
   LEOD_LAUNCH_CHECK();
   return 0;
 }

@@ -126,6 +126,7 @@ struct NtArgs {
   int acc_cols;   // TMEM columns per accumulator buffer (BN rounded up to 32)
   int tmem_cols;  // power of two >= 2 * acc_cols
   int staged;     // epilogue writes through shared memory (N multiple of 16: every chunk is full)
+  int kpb;        // implicit-GEMM taps (g.taps.n > 1): k-blocks per tap
 };
 
 // epilogue warps: a multiple of 4 (one TMEM lane quarter each); the column range of a tile is split between the warps that
@@ -156,6 +157,13 @@ __device__ __forceinline__ void nt_epilogue_chunk(const GemmNT &g, const uint32_
       for (int j = 0; j < 16; ++j)
         if (j < nvalid) v[j] += g.bias[n + j];
     }
+  }
+  if (g.out_f32) {
+    float *cx = (float *)g.C + (size_t)m * g.ldc + n;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) cx[j] = v[j];
+    return;
   }
   if (nvalid == 16) {
     if (g.epi == EPI_GELU) {
@@ -361,7 +369,13 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
           const uint32_t fb = smem_u32(&full_bar[s]);
           mbar_expect_tx(fb, stage_bytes);
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + A_STAGE_BYTES;
-          if (kb < a.nkb1) {
+          if (a.kpb > 0) {
+            // implicit-GEMM tap: the A tile is the same 128 rows shifted by the tap's row offset (rows outside the
+            // matrix are zero-filled by TMA), the B tile is that tap's column block of the weight
+            const int tap = kb / a.kpb, kc = kb - tap * a.kpb;
+            tma_load_2d(sa, &mapA, fb, kc * TILE_K, m0 + a.g.taps.off[tap]);
+            tma_load_2d(sb, &mapB, fb, tap * a.g.taps.cinp + kc * TILE_K, n0);
+          } else if (kb < a.nkb1) {
             tma_load_2d(sa, &mapA, fb, kb * TILE_K, m0);
             tma_load_2d(sb, &mapB, fb, kb * TILE_K, n0);
           } else {
@@ -562,6 +576,8 @@ struct TnArgs {
   int rows_per_split; // multiple of 64
   int stages;
   int tmem_cols;
+  ConvTaps taps;      // taps.n > 1: blockIdx.y also enumerates taps; X rows shifted by the tap offset, dW column block per tap
+  int tiles_k;
 };
 
 constexpr int TN_BOX_BYTES = 64 * 64 * 2;  // 64 tokens x 64 elements
@@ -576,7 +592,9 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
   uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages;
   uint32_t *tmem_slot = (uint32_t *)(bars + 2 * a.stages + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * TILE_M, k0 = blockIdx.y * a.BKt;
+  const int tap = blockIdx.y / a.tiles_k;
+  const int n0 = blockIdx.x * TILE_M, k0 = (blockIdx.y - tap * a.tiles_k) * a.BKt;
+  const int xoff = a.taps.n > 1 ? a.taps.off[tap] : 0;
   const int m_begin = blockIdx.z * a.rows_per_split;
   const int m_end = min(a.M, m_begin + a.rows_per_split);
   const int nkb = (m_end - m_begin + 63) / 64;
@@ -613,7 +631,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
         // split boundaries are multiples of 64, so only the global tail is ever partial
         tma_load_2d(sa, &mapY, fb, n0, m);
         tma_load_2d(sa + TN_BOX_BYTES, &mapY, fb, n0 + 64, m);
-        for (int j = 0; j < nbx; ++j) tma_load_2d(sa + (2 + j) * TN_BOX_BYTES, &mapX, fb, k0 + 64 * j, m);
+        for (int j = 0; j < nbx; ++j) tma_load_2d(sa + (2 + j) * TN_BOX_BYTES, &mapX, fb, k0 + 64 * j, m + xoff);
       }
     }
   } else if (warp == 1) {
@@ -644,7 +662,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
       if (n >= a.N) continue;
-      float *dst = a.dW + (size_t)n * a.ldw + k0 + c;
+      float *dst = a.dW + (size_t)n * a.ldw + (a.taps.n > 1 ? tap * a.taps.cinp : 0) + k0 + c;
       if (gridDim.z == 1 && k0 + c + 16 <= a.K && (((uintptr_t)dst) & 15) == 0) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -1349,9 +1367,13 @@ static int num_sms() {
 int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
   LEOD_REQUIRE(g.K > 0, "gemm_nt_tc: K = %d", g.K);
-  LEOD_REQUIRE(g.ldc % 8 == 0 && (!g.R || g.ldr % 8 == 0) && (!g.aux || g.ldaux % 8 == 0),
+  LEOD_REQUIRE(g.out_f32 || (g.ldc % 8 == 0 && (!g.R || g.ldr % 8 == 0) && (!g.aux || g.ldaux % 8 == 0)),
                "gemm_nt_tc: output/residual pitches must be multiples of 8 elements");
-  LEOD_REQUIRE((((uintptr_t)g.C) & 15) == 0, "gemm_nt_tc: C not 16-byte aligned");
+  LEOD_REQUIRE(g.out_f32 || (((uintptr_t)g.C) & 15) == 0, "gemm_nt_tc: C not 16-byte aligned");
+  LEOD_REQUIRE(!g.out_f32 || g.epi == EPI_NONE, "gemm_nt_tc: fp32 output has no fused epilogue");
+  const bool tapped = g.taps.n > 1;
+  LEOD_REQUIRE(!tapped || (!g.A2 && g.taps.n <= 9 && g.taps.cinp % TILE_K == 0 && g.taps.cin <= g.taps.cinp && g.K == g.taps.n * g.taps.cinp),
+               "gemm_nt_tc: bad tap description (n %d cin %d cinp %d K %d)", g.taps.n, g.taps.cin, g.taps.cinp, g.K);
   NtArgs a;
   a.g = g;
   a.BN = pick_bn(g.M, g.N, g.K);
@@ -1359,6 +1381,7 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   LEOD_REQUIRE(K1 > 0 && K2 >= 0 && (K2 == 0 || K1 % 8 == 0), "gemm_nt_tc: bad K split %d/%d", K1, g.K);
   a.nkb1 = ceil_div(K1, TILE_K);
   a.nkb = a.nkb1 + (K2 > 0 ? ceil_div(K2, TILE_K) : 0);
+  a.kpb = tapped ? g.taps.cinp / TILE_K : 0;
   a.tiles_m = ceil_div(g.M, TILE_M);
   a.tiles_n = ceil_div(g.N, a.BN);
   a.acc_cols = (int)round_up(a.BN, 32);
@@ -1366,14 +1389,14 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   while (a.tmem_cols < 2 * a.acc_cols) a.tmem_cols *= 2;
   const int stage_bytes = A_STAGE_BYTES + a.BN * TILE_K * 2;
   const int total_kb = a.nkb * ceil_div(a.tiles_m * a.tiles_n, num_sms());
-  a.staged = (g.N % 16 == 0 && (((uintptr_t)g.bias) & 15) == 0) ? 1 : 0;
+  a.staged = (g.N % 16 == 0 && (((uintptr_t)g.bias) & 15) == 0 && !g.out_f32) ? 1 : 0;
   const bool gelu_like = a.staged && g.epi == EPI_GELU;
   const int epi_warps = gelu_like ? NtEpiWarps<EPI_GELU>::value : 8;
   const int epi_bytes = epi_warps * ((a.staged && g.epi == EPI_GELU) ? 8192 : 4096) + 256;
   a.stages = std::min(std::min(4, (int)((224 * 1024 - epi_bytes - 2048) / stage_bytes)), std::max(total_kb, 1));
   CUtensorMap mA, mA2, mB, mB2;
-  LEOD_TRY(make_map(&mA, g.A, K1, g.M, g.lda, TILE_K, TILE_M));
-  LEOD_TRY(make_map(&mB, g.B, K1, g.N, g.ldb, TILE_K, a.BN));
+  LEOD_TRY(make_map(&mA, g.A, tapped ? g.taps.cin : K1, g.M, g.lda, TILE_K, TILE_M));
+  LEOD_TRY(make_map(&mB, g.B, tapped ? g.K : K1, g.N, g.ldb, TILE_K, a.BN));
   if (K2 > 0) {
     LEOD_TRY(make_map(&mA2, g.A2, K2, g.M, g.lda2, TILE_K, TILE_M));
     LEOD_TRY(make_map(&mB2, (const bf16 *)g.B + K1, K2, g.N, g.ldb, TILE_K, a.BN));
@@ -1495,19 +1518,22 @@ int lstm_seq_bwd_tc(const void *gates, const void *c_all, const void *c0, const 
 }
 
 int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias, int M, int N, int K,
-               cudaStream_t st) {
+               cudaStream_t st, const ConvTaps *taps) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (ldy % 8 != 0 || ldx % 8 != 0 || (((uintptr_t)dY | (uintptr_t)X) & 15) != 0) {
     // TMA needs 16-byte aligned rows: odd shapes (never produced by the backbone) take the SIMT kernel
-    return gemm_tn_simt(LEOD_BF16, dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, st);
+    return gemm_tn_simt(LEOD_BF16, dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, st, taps);
   }
   TnArgs a;
+  if (taps) a.taps = *taps;
+  const int ntap = a.taps.n > 1 ? a.taps.n : 1;
   a.dW = dW; a.ldw = ldw; a.M = M; a.N = N; a.K = K;
   a.BKt = K >= 256 ? 256 : (int)round_up(K, 64);
   const int tn = ceil_div(N, TILE_M), tk = ceil_div(K, a.BKt);
   // each split ends in an atomic epilogue over the whole output tile, so splits are only worth it when
   // they still stream a few thousand rows each; small-M problems run unsplit (plain read-modify-write)
-  int splits = ceil_div(148, tn * tk);
+  a.tiles_k = tk;
+  int splits = ceil_div(148, tn * tk * ntap);
   const int max_splits = M <= 4096 ? 1 : ceil_div(M, 2048);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -1527,7 +1553,7 @@ int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int l
     LEOD_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     attr_set = true;
   }
-  dim3 grid(tn, tk, splits);
+  dim3 grid(tn, tk * ntap, splits);
   gemm_tn_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(mY, mX, a);
   LEOD_LAUNCH_CHECK();
   if (dbias) {

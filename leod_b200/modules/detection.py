@@ -218,22 +218,9 @@ class FlatOptimizer:
         self.lr, self.wd, self.clip, self.betas, self.eps = lr, weight_decay, clip_value, betas, eps
         self.step_count = 0
         self.ema_alpha = ema_alpha
-        bb = detector.backbone
-        rest = [p for n, p in detector.named_parameters() if not n.startswith('backbone.')]
-        self.rest = rest
-        dev = bb.flat_params.device
-        n = sum(p.numel() for p in rest)
-        self.rest_flat = torch.empty(n, dtype=torch.float32, device=dev)
-        self.rest_grad = torch.zeros(n, dtype=torch.float32, device=dev)
-        off = 0
-        with torch.no_grad():
-            for p in rest:
-                k = p.numel()
-                self.rest_flat[off:off + k].copy_(p.reshape(-1))
-                p.data = self.rest_flat[off:off + k].view(p.shape)
-                p.grad = self.rest_grad[off:off + k].view(p.shape)
-                off += k
-        self.bufs = [(bb.flat_params, bb.flat_grads), (self.rest_flat, self.rest_grad)]
+        bb, de = detector.backbone, detector.detect_engine
+        # two flat fp32 buffers hold every parameter: the backbone's and the neck+head's (the nn.Parameters are views)
+        self.bufs = [(bb.flat_params, bb.flat_grads), (de.flat_params, de.flat_grads)]
         self.m = [torch.zeros_like(p) for p, _ in self.bufs]
         self.v = [torch.zeros_like(p) for p, _ in self.bufs]
         self.ema = [p.clone() for p, _ in self.bufs] if ema else [None, None]
@@ -250,3 +237,4 @@ class FlatOptimizer:
             fused_adamw_ema(p, g, m, v, step=self.step_count, lr=self.lr if lr is None else lr, beta1=self.betas[0],
                             beta2=self.betas[1], eps=self.eps, weight_decay=self.wd, clip_value=self.clip, ema=e, ema_alpha=a)
         self.detector.backbone.mark_params_updated()
+        self.detector.detect_engine.mark_params_updated()

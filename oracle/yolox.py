@@ -194,14 +194,19 @@ def iou_loss_elem(pred: torch.Tensor, tgt: torch.Tensor) -> torch.Tensor:
     return 1 - (inter / (union + 1e-16)) ** 2
 
 
-def yolox_losses(train_out: torch.Tensor, grid, labels: torch.Tensor, cfg: ModelCfg) -> Dict[str, torch.Tensor]:
+def yolox_losses(train_out: torch.Tensor, grid, labels: torch.Tensor, cfg: ModelCfg,
+                 forced_assign: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """yolo_head.py:403-597 / 776-972.  train_out [B,A,5+C]: decoded boxes, obj/cls LOGITS.
-    labels [B,N,7] zero-padded at the end of dim 1."""
+    labels [B,N,7] zero-padded at the end of dim 1.
+    forced_assign (test hook, not in the reference): [B,A] label-row index per anchor (-1 = background) that replaces the
+    SimOTA matching, so a reduced-precision implementation can be compared through the smooth part of the loss with its
+    own (possibly flipped) discrete assignment."""
     labels = apply_ignore_thresh(labels, cfg)
     B, A, _ = train_out.shape
     C = cfg.num_classes
     fg_all = torch.zeros(B, A, dtype=torch.bool)
     ign_all = torch.zeros(B, A, dtype=torch.bool)
+    matched_all = torch.full((B, A), -1, dtype=torch.long)
     reg_t = torch.zeros(B, A, 4)
     cls_t = torch.zeros(B, A, C)
     num_gts = 0
@@ -212,7 +217,15 @@ def yolox_losses(train_out: torch.Tensor, grid, labels: torch.Tensor, cfg: Model
         if n_all == 0:
             continue
         fg, matched, miou, ign = simota_assign(rows, train_out[b].detach(), grid, cfg)
+        if forced_assign is not None:
+            matched = forced_assign[b].long()
+            fg = matched >= 0
+            miou = torch.zeros(A)
+            if fg.any():
+                pi = pairwise_iou_cxcywh(rows[matched[fg], 1:5].float(), train_out[b, fg, :4].detach().float())
+                miou[fg] = pi.diagonal()
         fg_all[b], ign_all[b] = fg, ign
+        matched_all[b] = torch.where(fg, matched, torch.full_like(matched, -1))
         if fg.any():
             m = matched[fg]
             reg_t[b, fg] = rows[m, 1:5].float()
@@ -229,11 +242,11 @@ def yolox_losses(train_out: torch.Tensor, grid, labels: torch.Tensor, cfg: Model
     loss_cls = cfg.cls_weight * loss_cls
     return {'loss': loss_iou + loss_obj + loss_cls, 'iou_loss': loss_iou, 'conf_loss': loss_obj,
             'cls_loss': loss_cls, 'l1_loss': 0.0, 'num_fg': num_fg / max(num_gts, 1),
-            '_fg_mask': fg_all, '_ignore_mask': ign_all}
+            '_fg_mask': fg_all, '_ignore_mask': ign_all, '_matched': matched_all}
 
 
 def detect_forward(feats: Dict[int, torch.Tensor], sd, cfg: ModelCfg, targets: Optional[torch.Tensor] = None,
-                   training: bool = False, bn_state=None):
+                   training: bool = False, bn_state=None, forced_assign: Optional[torch.Tensor] = None):
     """detector.py:55-77 + yolo_head.py:195-287.  Returns (decoded predictions [B,A,5+C] with
     sigmoid scores, losses or None)."""
     kw = dict(training=training, bn_state=bn_state)
@@ -243,6 +256,6 @@ def detect_forward(feats: Dict[int, torch.Tensor], sd, cfg: ModelCfg, targets: O
     if training:
         assert targets is not None
         train_out, grid = flatten_decode(raw, strides, sigmoid_scores=False)
-        losses = yolox_losses(train_out, grid, targets, cfg)
+        losses = yolox_losses(train_out, grid, targets, cfg, forced_assign=forced_assign)
     preds, _ = flatten_decode(raw, strides, sigmoid_scores=True)
     return preds, losses

@@ -9,10 +9,6 @@ from test_host_cpu import product_cfg
 
 pytestmark = pytest.mark.gpu
 
-# the fp32 path is checked at 1e-3: keep cuDNN / cuBLAS (the torch-side neck and head) out of TF32
-torch.backends.cudnn.allow_tf32 = False
-torch.backends.cuda.matmul.allow_tf32 = False
-
 # The fixture network has O(1) LayerScale (0.25-0.75 instead of the 1e-5 init) and random weights on purpose: it
 # amplifies every rounding error.  fp32 path: ~2e-6 measured; bf16 path (bf16 residual stream, fp32 accumulation):
 # features 1-3 %, worst parameter gradient 8 % with a 1.7 % median on this adversarial network.
@@ -212,40 +208,6 @@ def test_training_step_module_sequence_vs_per_step(net):
     ref = float(z['train_plain/loss'])
     assert abs(out[False][0] - ref) < 1e-3 * abs(ref) and abs(out[True][0] - ref) < 1e-3 * abs(ref)
     assert rel_err(out[True][1], out[False][1]) < 1e-4
-
-
-def test_graphed_detect_equals_eager(net):
-    """forward_detect with graph_detect=True (neck+head+loss fwd/bwd replayed from a CUDA graph) gives the same losses,
-    parameter gradients, feature gradients and BatchNorm running statistics as the eager path, on two different inputs
-    (the second one is a pure replay)."""
-    z, cfg, sd, d = net
-    lab = torch.from_numpy(z['train_plain/labels']).cuda()
-    res = {}
-    for graphed in (False, True):
-        m = build(cfg, sd, (d['H'], d['W']), 'fp32').train()
-        m.graph_detect = graphed
-        gen = torch.Generator(device='cuda').manual_seed(3)
-        outs = []
-        for it in range(2):
-            m.zero_grad(set_to_none=True)
-            B = lab.shape[0]
-            shapes = m.backbone._state_shapes(B)
-            feats = {s + 1: torch.randn(shapes[s], device='cuda', generator=gen).requires_grad_(True) for s in (1, 2, 3)}
-            preds, losses = m.forward_detect(feats, targets=lab if it == 0 else lab.flip(0))
-            losses['loss'].backward()
-            torch.cuda.synchronize()
-            outs.append(dict(loss=float(losses['loss']), iou=float(losses['iou_loss']), preds=preds.detach().clone(),
-                             dfeat=[feats[k].grad.clone() for k in feats],
-                             pg=torch.cat([p.grad.reshape(-1) for n, p in m.named_parameters() if not n.startswith('backbone.')]),
-                             bn=torch.cat([b.reshape(-1).float() for n, b in m.named_buffers() if 'running' in n])))
-        res[graphed] = outs
-    for a, b in zip(res[False], res[True]):
-        assert abs(a['loss'] - b['loss']) < 1e-4 * abs(a['loss']) and abs(a['iou'] - b['iou']) < 1e-4 * max(1.0, abs(a['iou']))
-        assert rel_err(b['preds'], a['preds']) < 1e-5
-        assert rel_err(b['pg'], a['pg']) < 1e-4
-        assert rel_err(b['bn'], a['bn']) < 1e-5
-        for ga, gb_ in zip(a['dfeat'], b['dfeat']):
-            assert rel_err(gb_, ga) < 1e-4
 
 
 def test_gradient_accumulation_and_zero_grad(net):
