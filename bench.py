@@ -254,7 +254,6 @@ def main():
                     help='train: BASELINE configs[1] (the headline metric); sweep: teacher pseudo-label sweep, configs[3] shape')
     ap.add_argument('--e2e-lag', type=int, default=2, help='the loss of step i is read back on the host after step i+lag was enqueued')
     ap.add_argument('--copy-streams', type=int, default=4, help='streams the per-step host->device upload is split over (e2e leg)')
-    ap.add_argument('--no-graph-head', action='store_true', help='run neck/head/loss eagerly instead of replaying a CUDA graph')
     ap.add_argument('--phases', action='store_true', help='after the timed regions, time the phases of 3 extra steps (stderr)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -280,12 +279,9 @@ def main():
     full_cfg = Node(model=make_model_cfg(size='small', dataset='gen1', compute_dtype=args.dtype),
                     dataset=dict(sequence_length=L, name='gen1'))
     module = Module(full_cfg)
-    if world > 1:  # the reference trains with sync_batchnorm under DDP (train.py:247)
-        module.mdl.fpn = torch.nn.SyncBatchNorm.convert_sync_batchnorm(module.mdl.fpn)
-        module.mdl.yolox_head = torch.nn.SyncBatchNorm.convert_sync_batchnorm(module.mdl.yolox_head)
     module.to(dev).train()
-    # neck + head + loss fwd/bwd as one CUDA-graph replay (for N > 1 the SyncBatchNorm collectives are captured too)
-    module.mdl.graph_detect = not args.no_graph_head
+    if world > 1:  # the reference trains with sync_batchnorm under DDP (train.py:247): one statistics exchange per dependency level
+        module.mdl.detect_engine.set_sync_batchnorm()
     bb = module.mdl.backbone
     if args.gemm_impl is not None:
         bb.set_gemm_impl(args.gemm_impl)
@@ -294,7 +290,9 @@ def main():
         from leod_b200.modules.utils.distributed import allreduce_mean_, broadcast_flat
         broadcast_flat([p for p, _ in opt.bufs], src=0)      # identical replicas, as DDP's initial broadcast
         bb.mark_params_updated()
+        module.mdl.detect_engine.mark_params_updated()
         bb.grad_sync = lambda flat_grad: allreduce_mean_([flat_grad])
+        module.mdl.detect_engine.grad_sync = lambda flat_grad: allreduce_mean_([flat_grad])
 
     # several distinct batches so consecutive steps do not re-read the same 25 MB of input
     n_batches = 4
@@ -305,8 +303,6 @@ def main():
         opt.zero_grad()
         out = module.training_step(make_batch(ev_dev, labels, first))
         out['loss'].backward()
-        if world > 1:
-            allreduce_mean_([opt.rest_grad])
         opt.step()
         return out['loss']
 
@@ -512,8 +508,6 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'event-frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
             'gpu_launches': int(launches), 'host_enqueue_ms_per_step': host_enqueue_ms, 'roofline': roof, 'cpu_baseline': cpu, 'clocks': clocks, 'loss': loss_host}))
     if world > 1:
-        # captured graphs hold NCCL work: drop them before tearing the process group down, and never hang at exit
-        module.mdl._detect_graphs.clear()
         dist.barrier()
         torch.cuda.synchronize()
         sys.stdout.flush()

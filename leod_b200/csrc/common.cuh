@@ -180,14 +180,21 @@ int im2col_pad_s2(int dtype, const void *src, int lds, const PadGeom &gs, void *
                   cudaStream_t st);
 int col2im_pad_s2(int dtype, const void *dcol, int ldcol, const PadGeom &go, void *dsrc, int lds, const PadGeom &gs, int cin, int cinp,
                   int accumulate, cudaStream_t st);
-int bn_stats(int dtype, const void *Y, int ldy, const PadGeom &g, int C, double *stats, cudaStream_t st);
-int bn_apply_silu(int dtype, const void *Y, int ldy, const PadGeom &g, int C, const double *stats, const BnSeg &s0, const BnSeg &s1, int cseg,
-                  void *Z, int ldz, float eps, float momentum, int training, cudaStream_t st);
-int bn_bwd_reduce(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, int C, const double *stats, const BnSeg &s0,
-                  const BnSeg &s1, int cseg, float eps, double *dstat, cudaStream_t st);
-int bn_bwd_apply(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, int C, const double *stats,
-                 const double *dstat_global, const double *dstat_local, const BnSeg &s0, const BnSeg &s1, int cseg, float eps, void *dY, int lddy,
-                 cudaStream_t st);
+// One BatchNorm layer's buffers.  stats (double): [0,C) sum, [C,2C) sum of squares, [2C] count, [2C+1] ticket.  fin (float): mean, rstd.
+// dloc / dglob (double): [0,C) sum dyhat, [C,2C) sum dyhat*xhat, [2C] ticket (local / over all ranks).  dfin (float): the two means.
+struct BnLayer {
+  int C = 0, cseg = 0;
+  BnSeg s0, s1;
+  double *stats = nullptr, *dloc = nullptr, *dglob = nullptr;
+  float *fin = nullptr, *dfin = nullptr;
+  float eps = 1e-5f, momentum = 0.1f;
+};
+int bn_stats(int dtype, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, int finalize, cudaStream_t st);
+int bn_finalize(const BnLayer &l, cudaStream_t st);
+int bn_apply_silu(int dtype, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, void *Z, int ldz, int training, cudaStream_t st);
+int bn_bwd_reduce(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, int finalize, cudaStream_t st);
+int bn_bwd_finalize(const BnLayer &l, cudaStream_t st);
+int bn_bwd_apply(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, void *dY, int lddy, cudaStream_t st);
 int device_zero_bytes(void *p, size_t bytes, cudaStream_t st);
 
 // ------------------------------------------------------------------ head decode + SimOTA loss (kernels_simota.cu)

@@ -50,8 +50,11 @@ struct Conv {
   bool use_G = false;      // weight gradient goes through a prepared-layout scratch (3x3 / rotated), else straight into grads
   void *Wp = nullptr, *WpT = nullptr;
   float *G = nullptr;
-  void *Y = nullptr;
+  void *Y = nullptr, *dY = nullptr;   // raw convolution output / its gradient (both kept per layer: the weight-gradient GEMM of a
+                                      // layer runs on a side stream while the main stream already works on the next layer)
+  cudaEvent_t ev_dy = nullptr;
   double *stats = nullptr, *dloc = nullptr, *dglob = nullptr;
+  float *fin = nullptr, *dfin = nullptr;   // mean | rstd  and  mean(dyhat) | mean(dyhat * xhat), see kernels_conv.cu
 };
 
 struct Pred {     // the three 1x1 prediction convolutions of one level (yolo_head.py:214-222) as one GEMM
@@ -90,6 +93,12 @@ struct leod_detect {
   Pred pred[3];
   int x_act[3], x_off[3];        // where the three backbone features are gathered to (x2, x1, x0)
   int t2_act[3];
+  int head_convs[3][4];          // per level: stem, fused first tower convolutions, cls tower 2nd, reg tower 2nd
+  size_t n_neck_ops = 0;         // ops[0 .. n_neck_ops) = neck, the rest = head phases (used when statistics are exchanged)
+  cudaStream_t lvl_stream[2] = {nullptr, nullptr};   // head levels 1, 2 (level 0 runs on the caller's stream)
+  cudaStream_t wg_stream[2] = {nullptr, nullptr};    // weight-gradient GEMMs
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  int wg_next = 0;
   float *params = nullptr, *grads = nullptr, *buffers = nullptr;
   long long *nbt = nullptr;
   bool layout_only = false;
@@ -100,7 +109,7 @@ struct leod_detect {
   // arena (sized for arena_B images)
   int arena_B = 0, cur_B = 0;
   void *arena = nullptr;
-  void *col = nullptr, *dcol = nullptr, *dY = nullptr;
+  void *col = nullptr, *dcol = nullptr;
   double *stats_all = nullptr, *dloc_all = nullptr, *dglob_all = nullptr;
   int64_t stats_doubles = 0, dstat_doubles = 0;
   float *tout = nullptr, *miou = nullptr, *losses = nullptr;
@@ -245,6 +254,10 @@ int build_graph(leod_detect *h) {
     cls2[l] = add_conv(h, "yolox_head.cls_convs." + L + ".1", "", 3, 1, hid, hid, l, t1[l], 0, h->t2_act[l], 0);
     reg2[l] = add_conv(h, "yolox_head.reg_convs." + L + ".1", "", 3, 1, hid, hid, l, t1[l], hid, h->t2_act[l], hid);
   }
+  for (int l = 0; l < 3; ++l) {
+    h->head_convs[l][0] = s_conv[l]; h->head_convs[l][1] = t1_conv[l]; h->head_convs[l][2] = cls2[l]; h->head_convs[l][3] = reg2[l];
+  }
+  h->n_neck_ops = h->ops.size();
   add_phase(h, {s_conv[0], s_conv[1], s_conv[2]});
   add_phase(h, {t1_conv[0], t1_conv[1], t1_conv[2]});
   add_phase(h, {cls2[0], reg2[0], cls2[1], reg2[1], cls2[2], reg2[2]});
@@ -423,31 +436,31 @@ int ensure_arena(leod_detect *h, int B) {
   };
   PadGeom g[3];
   for (int l = 0; l < 3; ++l) g[l] = make_pad_geom(B, h->lh[l], h->lw[l]);
-  std::vector<int64_t> az(h->acts.size()), adz(h->acts.size()), cy(h->convs.size());
+  std::vector<int64_t> az(h->acts.size()), adz(h->acts.size()), cy(h->convs.size()), cdy(h->convs.size());
   for (size_t i = 0; i < h->acts.size(); ++i) {
     az[i] = take(g[h->acts[i].level].R * h->acts[i].width * e);
     adz[i] = take(g[h->acts[i].level].R * h->acts[i].width * e);
   }
-  int64_t col_bytes = 0, dy_bytes = 0;
+  int64_t col_bytes = 0;
   for (size_t i = 0; i < h->convs.size(); ++i) {
     const Conv &c = h->convs[i];
     cy[i] = take(g[c.lev_out].R * c.cout * e);
-    dy_bytes = std::max(dy_bytes, g[c.lev_out].R * c.cout * e);
+    cdy[i] = take(g[c.lev_out].R * c.cout * e);
     if (c.stride == 2) col_bytes = std::max(col_bytes, g[c.lev_out].R * 9 * c.cinp * e);
   }
-  const int64_t o_col = take(col_bytes), o_dcol = take(col_bytes), o_dy = take(dy_bytes);
-  // statistics: forward [2*cout + 2] doubles per convolution in op order (a phase is one contiguous range), backward [2*cout]
+  const int64_t o_col = take(col_bytes), o_dcol = take(col_bytes);
+  // statistics: [2*cout + 4] doubles per convolution in op order (a phase is one contiguous range), forward and backward
   int64_t sd = 0, dd = 0;
   std::vector<int64_t> so(h->convs.size()), dof(h->convs.size());
   for (const Op &o : h->ops)
     if (o.kind == 0)
       for (int ci : o.convs) {
-        so[ci] = sd; sd += 2 * h->convs[ci].cout + 2;
-        dof[ci] = dd; dd += 2 * h->convs[ci].cout;
+        so[ci] = sd; sd += 2 * h->convs[ci].cout + 4;    // multiples of 4 entries: the float copies are read as float4
+        dof[ci] = dd; dd += 2 * h->convs[ci].cout + 4;
       }
   h->stats_doubles = sd;
   h->dstat_doubles = dd;
-  const int64_t o_stats = take(sd * 8), o_dloc = take(dd * 8), o_dglob = take(dd * 8);
+  const int64_t o_stats = take(sd * 8), o_dloc = take(dd * 8), o_dglob = take(dd * 8), o_fin = take(sd * 4), o_dfin = take(dd * 4);
   int64_t o_raw[3], o_draw[3];
   int A = 0;
   for (int l = 0; l < 3; ++l) {
@@ -468,11 +481,14 @@ int ensure_arena(leod_detect *h, int B) {
   for (size_t i = 0; i < h->convs.size(); ++i) {
     Conv &c = h->convs[i];
     c.Y = base + cy[i];
+    c.dY = base + cdy[i];
     c.stats = (double *)(base + o_stats) + so[i];
     c.dloc = (double *)(base + o_dloc) + dof[i];
     c.dglob = (double *)(base + o_dglob) + dof[i];
+    c.fin = (float *)(base + o_fin) + so[i];
+    c.dfin = (float *)(base + o_dfin) + dof[i];
   }
-  h->col = base + o_col; h->dcol = base + o_dcol; h->dY = base + o_dy;
+  h->col = base + o_col; h->dcol = base + o_dcol;
   h->stats_all = (double *)(base + o_stats); h->dloc_all = (double *)(base + o_dloc); h->dglob_all = (double *)(base + o_dglob);
   for (int l = 0; l < 3; ++l) {
     h->pred[l].raw = (float *)(base + o_raw[l]);
@@ -517,17 +533,24 @@ ConvTaps taps3x3(int w2, int cin, int cinp, int sign) {
   return t;
 }
 
-void bn_segs(const leod_detect *h, const Conv &c, BnSeg s[2], bool with_grads) {
+BnLayer bn_layer(const leod_detect *h, const Conv &c, bool with_grads) {
+  BnLayer l;
+  l.C = c.cout; l.cseg = c.cseg;
+  BnSeg *s[2] = {&l.s0, &l.s1};
   for (int i = 0; i < 2; ++i) {
     const int k = i < c.nseg ? i : 0;
-    s[i].gamma = h->params + c.bnw[k];
-    s[i].beta = h->params + c.bnb[k];
-    s[i].rmean = h->buffers ? h->buffers + c.rm[k] : nullptr;
-    s[i].rvar = h->buffers ? h->buffers + c.rv[k] : nullptr;
-    s[i].nbt = h->nbt ? h->nbt + c.nbt[k] : nullptr;
-    s[i].dgamma = with_grads ? h->grads + c.bnw[k] : nullptr;
-    s[i].dbeta = with_grads ? h->grads + c.bnb[k] : nullptr;
+    s[i]->gamma = h->params + c.bnw[k];
+    s[i]->beta = h->params + c.bnb[k];
+    s[i]->rmean = h->buffers ? h->buffers + c.rm[k] : nullptr;
+    s[i]->rvar = h->buffers ? h->buffers + c.rv[k] : nullptr;
+    s[i]->nbt = h->nbt ? h->nbt + c.nbt[k] : nullptr;
+    s[i]->dgamma = with_grads ? h->grads + c.bnw[k] : nullptr;
+    s[i]->dbeta = with_grads ? h->grads + c.bnb[k] : nullptr;
   }
+  l.stats = c.stats; l.dloc = c.dloc; l.dglob = h->allreduce ? c.dglob : c.dloc;
+  l.fin = c.fin; l.dfin = c.dfin;
+  l.eps = h->cfg.bn_eps; l.momentum = h->cfg.bn_momentum;
+  return l;
 }
 
 // convolution (+ batch statistics in training)
@@ -550,60 +573,117 @@ int conv_fwd_a(leod_detect *h, Conv &c, const PadGeom g[3], bool training, cudaS
   LEOD_TRY(gemm_nt(h, gm, st));
   if (training) {
     ProfScope ps(PK_OTHER, 0, (double)go.R * c.cout * h->esz(), st);
-    LEOD_TRY(bn_stats(dt, c.Y, c.cout, go, c.cout, c.stats, st));
+    LEOD_TRY(bn_stats(dt, c.Y, c.cout, go, bn_layer(h, c, false), h->allreduce ? 0 : 1, st));
   }
   return 0;
 }
 // BN-apply + SiLU into the consumer's matrix
 int conv_fwd_b(leod_detect *h, Conv &c, const PadGeom g[3], bool training, cudaStream_t st) {
-  BnSeg s[2];
-  bn_segs(h, c, s, false);
   const PadGeom &go = g[c.lev_out];
   ProfScope ps(PK_OTHER, 0, 2.0 * go.R * c.cout * h->esz(), st);
-  return bn_apply_silu(h->cfg.dtype, c.Y, c.cout, go, c.cout, c.stats, s[0], s[1], c.cseg, act_z(h, c.out_act, c.out_off),
-                       h->acts[c.out_act].width, h->cfg.bn_eps, h->cfg.bn_momentum, training ? 1 : 0, st);
+  return bn_apply_silu(h->cfg.dtype, c.Y, c.cout, go, bn_layer(h, c, false), act_z(h, c.out_act, c.out_off), h->acts[c.out_act].width,
+                       training ? 1 : 0, st);
 }
 int conv_bwd_a(leod_detect *h, Conv &c, const PadGeom g[3], cudaStream_t st) {
-  BnSeg s[2];
-  bn_segs(h, c, s, false);
   const PadGeom &go = g[c.lev_out];
   ProfScope ps(PK_OTHER, 0, 2.0 * go.R * c.cout * h->esz(), st);
-  return bn_bwd_reduce(h->cfg.dtype, act_dz(h, c.out_act, c.out_off), h->acts[c.out_act].width, c.Y, c.cout, go, c.cout, c.stats, s[0], s[1], c.cseg,
-                       h->cfg.bn_eps, c.dloc, st);
+  return bn_bwd_reduce(h->cfg.dtype, act_dz(h, c.out_act, c.out_off), h->acts[c.out_act].width, c.Y, c.cout, go, bn_layer(h, c, true),
+                       h->allreduce ? 0 : 1, st);
 }
+int ensure_streams(leod_detect *h) {
+  if (h->ev_fork) return 0;
+  for (int i = 0; i < 2; ++i) {
+    LEOD_CUDA(cudaStreamCreateWithFlags(&h->lvl_stream[i], cudaStreamNonBlocking));
+    LEOD_CUDA(cudaStreamCreateWithFlags(&h->wg_stream[i], cudaStreamNonBlocking));
+  }
+  for (int i = 0; i < 4; ++i) LEOD_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+  for (Conv &c : h->convs) LEOD_CUDA(cudaEventCreateWithFlags(&c.ev_dy, cudaEventDisableTiming));
+  LEOD_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  return 0;
+}
+
+// BN + SiLU backward (-> dY of this layer), the weight gradient on a side stream, the input gradient on `st`
 int conv_bwd_b(leod_detect *h, Conv &c, const PadGeom g[3], cudaStream_t st) {
   const int dt = h->cfg.dtype;
-  BnSeg s[2];
-  bn_segs(h, c, s, true);
   const PadGeom &gi = g[c.lev_in], &go = g[c.lev_out];
   const int taps = c.k * c.k;
   {
     ProfScope ps(PK_OTHER, 0, 3.0 * go.R * c.cout * h->esz(), st);
-    LEOD_TRY(bn_bwd_apply(dt, act_dz(h, c.out_act, c.out_off), h->acts[c.out_act].width, c.Y, c.cout, go, c.cout, c.stats,
-                          h->allreduce ? c.dglob : c.dloc, c.dloc, s[0], s[1], c.cseg, h->cfg.bn_eps, h->dY, c.cout, st));
+    LEOD_TRY(bn_bwd_apply(dt, act_dz(h, c.out_act, c.out_off), h->acts[c.out_act].width, c.Y, c.cout, go, bn_layer(h, c, true), c.dY, c.cout, st));
   }
   const void *X = act_z(h, c.in_act, c.in_off);
   const int ldx = h->acts[c.in_act].width;
   void *dX = act_dz(h, c.in_act, c.in_off);
   float *dW = c.use_G ? c.G : h->grads + c.w[0];
   const int ldw = c.use_G ? taps * c.cinp : c.cin;
-  if (c.stride == 2) {
+  if (c.stride == 2) {   // the patch matrix is a shared scratch: everything stays on the main stream (two layers only)
     LEOD_TRY(im2col_pad_s2(dt, X, ldx, gi, h->col, 9 * c.cinp, go, c.cin, c.cinp, st));
-    LEOD_TRY(gemm_tn(h, h->dY, c.cout, h->col, 9 * c.cinp, dW, ldw, nullptr, (int)go.R, c.cout, 9 * c.cinp, st));
-    LEOD_TRY(gemm_nt(h, plain(h->dY, c.cout, c.WpT, c.coutp, h->dcol, 9 * c.cinp, (int)go.R, 9 * c.cinp, c.cout), st));
+    LEOD_TRY(gemm_tn(h, c.dY, c.cout, h->col, 9 * c.cinp, dW, ldw, nullptr, (int)go.R, c.cout, 9 * c.cinp, st));
+    LEOD_TRY(gemm_nt(h, plain(c.dY, c.cout, c.WpT, c.coutp, h->dcol, 9 * c.cinp, (int)go.R, 9 * c.cinp, c.cout), st));
     LEOD_TRY(col2im_pad_s2(dt, h->dcol, 9 * c.cinp, go, dX, ldx, gi, c.cin, c.cinp, /*accumulate=*/1, st));
-  } else if (c.k == 3) {
+    return 0;
+  }
+  // weight gradient: off the critical path (nothing downstream in this backward pass reads it)
+  cudaStream_t ws = leod_profiling_on() ? st : h->wg_stream[h->wg_next];
+  if (ws != st) {
+    h->wg_next ^= 1;
+    LEOD_CUDA(cudaEventRecord(c.ev_dy, st));
+    LEOD_CUDA(cudaStreamWaitEvent(ws, c.ev_dy, 0));
+  }
+  if (c.k == 3) {
     const ConvTaps tw = taps3x3(go.w2, c.cin, c.cinp, +1);
-    LEOD_TRY(gemm_tn(h, h->dY, c.cout, X, ldx, dW, ldw, nullptr, (int)go.R, c.cout, c.cin, st, &tw));
-    GemmNT gm = plain(h->dY, c.cout, c.WpT, 9 * c.coutp, dX, ldx, (int)gi.R, c.cin, 9 * c.coutp);
+    LEOD_TRY(gemm_tn(h, c.dY, c.cout, X, ldx, dW, ldw, nullptr, (int)go.R, c.cout, c.cin, ws, &tw));
+    GemmNT gm = plain(c.dY, c.cout, c.WpT, 9 * c.coutp, dX, ldx, (int)gi.R, c.cin, 9 * c.coutp);
     gm.taps = taps3x3(go.w2, c.cout, c.coutp, -1);
     LEOD_TRY(gemm_nt(h, gm, st));
   } else {
-    LEOD_TRY(gemm_tn(h, h->dY, c.cout, X, ldx, dW, ldw, nullptr, (int)go.R, c.cout, c.cin, st));
-    LEOD_TRY(gemm_nt(h, plain(h->dY, c.cout, c.WpT, c.coutp, dX, ldx, (int)gi.R, c.cin, c.cout), st));
+    LEOD_TRY(gemm_tn(h, c.dY, c.cout, X, ldx, dW, ldw, nullptr, (int)go.R, c.cout, c.cin, ws));
+    LEOD_TRY(gemm_nt(h, plain(c.dY, c.cout, c.WpT, c.coutp, dX, ldx, (int)gi.R, c.cin, c.cout), st));
   }
   return 0;
 }
+
+// prediction GEMM of one level (yolo_head.py:214-222) and its backward
+int pred_fwd(leod_detect *h, int l, const PadGeom g[3], cudaStream_t st) {
+  Pred &p = h->pred[l];
+  GemmNT gm = plain(h->acts[p.in_act].z, 2 * h->hid, p.B, 2 * h->hid, p.raw, 8, (int)g[l].R, 5 + h->cfg.num_classes, 2 * h->hid);
+  gm.bias = p.bias;
+  gm.out_f32 = 1;
+  return gemm_nt(h, gm, st);
+}
+int pred_bwd(leod_detect *h, int l, const PadGeom g[3], cudaStream_t st) {
+  Pred &p = h->pred[l];
+  LEOD_TRY(gemm_tn(h, p.draw, 8, h->acts[p.in_act].z, 2 * h->hid, p.G, 2 * h->hid, p.gb, (int)g[l].R, 8, 2 * h->hid, st));
+  return gemm_nt(h, plain(p.draw, 8, p.BT, 8, h->acts[p.in_act].dz, 2 * h->hid, (int)g[l].R, 2 * h->hid, 8), st);
+}
+// one phase of convolutions on one stream (+ the statistics exchange in data-parallel mode)
+int phase_fwd(leod_detect *h, const Op &o, const PadGeom g[3], bool training, cudaStream_t st) {
+  for (int ci : o.convs) LEOD_TRY(conv_fwd_a(h, h->convs[ci], g, training, st));
+  if (training && h->allreduce) {
+    const Conv &first = h->convs[o.convs.front()], &last = h->convs[o.convs.back()];
+    const int64_t n = (last.stats + 2 * last.cout + 2) - first.stats;
+    LEOD_REQUIRE(h->allreduce(h->allreduce_ctx, first.stats, n, (void *)st) == 0, "leod_fpn_head_fwd: statistics all-reduce callback failed");
+    for (int ci : o.convs) LEOD_TRY(bn_finalize(bn_layer(h, h->convs[ci], false), st));
+  }
+  for (int ci : o.convs) LEOD_TRY(conv_fwd_b(h, h->convs[ci], g, training, st));
+  return 0;
+}
+int phase_bwd(leod_detect *h, const Op &o, const PadGeom g[3], cudaStream_t st) {
+  for (int ci : o.convs) LEOD_TRY(conv_bwd_a(h, h->convs[ci], g, st));
+  if (h->allreduce) {
+    const Conv &first = h->convs[o.convs.front()], &last = h->convs[o.convs.back()];
+    const int64_t n = (last.dloc + 2 * last.cout + 2) - first.dloc;
+    LEOD_TRY(device_copy(first.dglob, first.dloc, (size_t)n * 8, st));
+    LEOD_REQUIRE(h->allreduce(h->allreduce_ctx, first.dglob, n, (void *)st) == 0, "leod_fpn_head_bwd: statistics all-reduce callback failed");
+    for (int ci : o.convs) LEOD_TRY(bn_bwd_finalize(bn_layer(h, h->convs[ci], true), st));
+  }
+  // the members of a phase write disjoint gradient matrices (the twin towers' second convolutions: disjoint column halves)
+  for (int ci : o.convs) LEOD_TRY(conv_bwd_b(h, h->convs[ci], g, st));
+  return 0;
+}
+// The three pyramid levels of the head are independent chains of small kernels: in a single process they run side by side on
+// three streams.  With a statistics exchange they run phase by phase on one stream so that every rank issues the same collectives.
+bool head_multi_stream(const leod_detect *h) { return !h->allreduce && !leod_profiling_on(); }
 
 void geoms(const leod_detect *h, int B, PadGeom g[3]) {
   for (int l = 0; l < 3; ++l) g[l] = make_pad_geom(B, h->lh[l], h->lw[l]);
@@ -666,6 +746,15 @@ extern "C" void leod_detect_destroy(leod_detect_t *h) {
   if (!h) return;
   for (void *p : h->owned) cudaFree(p);
   if (h->arena) cudaFree(h->arena);
+  for (int i = 0; i < 2; ++i) {
+    if (h->lvl_stream[i]) cudaStreamDestroy(h->lvl_stream[i]);
+    if (h->wg_stream[i]) cudaStreamDestroy(h->wg_stream[i]);
+  }
+  for (int i = 0; i < 4; ++i)
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (auto &c : h->convs)
+    if (c.ev_dy) cudaEventDestroy(c.ev_dy);
   delete h;
 }
 extern "C" int leod_detect_param_info(const leod_detect_t *h, int i, char *name, size_t cap, int64_t *offset, int32_t *ndim, int64_t shape[4]) {
@@ -736,30 +825,38 @@ extern "C" int leod_fpn_head_fwd(leod_detect_t *h, const void *const feats[3], i
     ProfScope ps(PK_OTHER, 0, 2.0 * g[l].R * h->cfg.in_channels[l] * h->esz(), st);
     LEOD_TRY(pad_gather(dt, feats[l], act_z(h, h->x_act[l], h->x_off[l]), h->acts[h->x_act[l]].width, g[l], h->cfg.in_channels[l], st));
   }
-  for (const Op &o : h->ops) {
+  LEOD_TRY(ensure_streams(h));
+  const bool multi = head_multi_stream(h);
+  const size_t n_ops = multi ? h->n_neck_ops : h->ops.size();
+  for (size_t oi = 0; oi < n_ops; ++oi) {
+    const Op &o = h->ops[oi];
     if (o.kind == 1) {
       const Act &s = h->acts[o.src_act], &d = h->acts[o.dst_act];
       ProfScope ps(PK_OTHER, 0, 1.25 * g[d.level].R * o.C * h->esz(), st);
       LEOD_TRY(upsample2x(dt, act_z(h, o.src_act, o.src_off), s.width, g[s.level], act_z(h, o.dst_act, o.dst_off), d.width, g[d.level], o.C, st));
       continue;
     }
-    for (int ci : o.convs) LEOD_TRY(conv_fwd_a(h, h->convs[ci], g, training != 0, st));
-    if (training && h->allreduce) {
-      const Conv &first = h->convs[o.convs.front()], &last = h->convs[o.convs.back()];
-      const int64_t n = (last.stats + 2 * last.cout + 2) - first.stats;
-      LEOD_REQUIRE(h->allreduce(h->allreduce_ctx, first.stats, n, stream) == 0, "leod_fpn_head_fwd: statistics all-reduce callback failed");
-    }
-    for (int ci : o.convs) LEOD_TRY(conv_fwd_b(h, h->convs[ci], g, training != 0, st));
+    LEOD_TRY(phase_fwd(h, o, g, training != 0, st));
   }
-  const int N = 5 + h->cfg.num_classes;
   HeadPtrs rp;
-  for (int l = 0; l < 3; ++l) {
-    Pred &p = h->pred[l];
-    GemmNT gm = plain(h->acts[p.in_act].z, 2 * h->hid, p.B, 2 * h->hid, p.raw, 8, (int)g[l].R, N, 2 * h->hid);
-    gm.bias = p.bias;
-    gm.out_f32 = 1;
-    LEOD_TRY(gemm_nt(h, gm, st));
-    rp.raw[l] = p.raw;
+  for (int l = 0; l < 3; ++l) rp.raw[l] = h->pred[l].raw;
+  if (multi) {
+    LEOD_CUDA(cudaEventRecord(h->ev_fork, st));
+    for (int l = 2; l >= 0; --l) {   // the small levels first: their chains are pure latency
+      cudaStream_t sl = l == 0 ? st : h->lvl_stream[l - 1];
+      if (l > 0) LEOD_CUDA(cudaStreamWaitEvent(sl, h->ev_fork, 0));
+      for (int k = 0; k < 4; ++k) {
+        Op o;
+        o.kind = 0;
+        o.convs.assign(1, h->head_convs[l][k]);
+        LEOD_TRY(phase_fwd(h, o, g, training != 0, sl));
+      }
+      LEOD_TRY(pred_fwd(h, l, g, sl));
+      if (l > 0) LEOD_CUDA(cudaEventRecord(h->ev_join[l - 1], sl));
+    }
+    for (int l = 1; l < 3; ++l) LEOD_CUDA(cudaStreamWaitEvent(st, h->ev_join[l - 1], 0));
+  } else {
+    for (int l = 0; l < 3; ++l) LEOD_TRY(pred_fwd(h, l, g, st));
   }
   if (training) h->train_gen = h->fwd_gen;
   // eval: decode only; training: the decoded/logit copy and the geometry flags are produced by leod_simota_loss_fwd
@@ -847,13 +944,29 @@ extern "C" int leod_fpn_head_bwd(leod_detect_t *h, void *const dfeats[3], void *
   PadGeom g[3];
   geoms(h, B, g);
   LEOD_TRY(device_zero_bytes(h->dloc_all, (size_t)h->dstat_doubles * 8, st));
-  for (int l = 0; l < 3; ++l) {
-    Pred &p = h->pred[l];
-    const void *t2 = h->acts[p.in_act].z;
-    LEOD_TRY(gemm_tn(h, p.draw, 8, t2, 2 * h->hid, p.G, 2 * h->hid, p.gb, (int)g[l].R, 8, 2 * h->hid, st));
-    LEOD_TRY(gemm_nt(h, plain(p.draw, 8, p.BT, 8, h->acts[p.in_act].dz, 2 * h->hid, (int)g[l].R, 2 * h->hid, 8), st));
+  LEOD_TRY(ensure_streams(h));
+  const bool multi = head_multi_stream(h);
+  size_t n_ops = h->ops.size();
+  if (multi) {
+    n_ops = h->n_neck_ops;
+    LEOD_CUDA(cudaEventRecord(h->ev_fork, st));
+    for (int l = 2; l >= 0; --l) {
+      cudaStream_t sl = l == 0 ? st : h->lvl_stream[l - 1];
+      if (l > 0) LEOD_CUDA(cudaStreamWaitEvent(sl, h->ev_fork, 0));
+      LEOD_TRY(pred_bwd(h, l, g, sl));
+      for (int k = 3; k >= 0; --k) {
+        Op o;
+        o.kind = 0;
+        o.convs.assign(1, h->head_convs[l][k]);
+        LEOD_TRY(phase_bwd(h, o, g, sl));
+      }
+      if (l > 0) LEOD_CUDA(cudaEventRecord(h->ev_join[l - 1], sl));
+    }
+    for (int l = 1; l < 3; ++l) LEOD_CUDA(cudaStreamWaitEvent(st, h->ev_join[l - 1], 0));
+  } else {
+    for (int l = 0; l < 3; ++l) LEOD_TRY(pred_bwd(h, l, g, st));
   }
-  for (int oi = (int)h->ops.size() - 1; oi >= 0; --oi) {
+  for (int oi = (int)n_ops - 1; oi >= 0; --oi) {
     const Op &o = h->ops[oi];
     if (o.kind == 1) {
       const Act &s = h->acts[o.src_act], &d = h->acts[o.dst_act];
@@ -862,16 +975,11 @@ extern "C" int leod_fpn_head_bwd(leod_detect_t *h, void *const dfeats[3], void *
                               /*accumulate=*/1, st));
       continue;
     }
-    for (int ci : o.convs) LEOD_TRY(conv_bwd_a(h, h->convs[ci], g, st));
-    if (h->allreduce) {
-      const Conv &first = h->convs[o.convs.front()], &last = h->convs[o.convs.back()];
-      const int64_t n = (last.dloc + 2 * last.cout) - first.dloc;
-      LEOD_TRY(device_copy(first.dglob, first.dloc, (size_t)n * 8, st));
-      LEOD_REQUIRE(h->allreduce(h->allreduce_ctx, first.dglob, n, stream) == 0, "leod_fpn_head_bwd: statistics all-reduce callback failed");
-    }
-    // the members of a phase write disjoint gradient matrices except the twin towers' second convolutions, which write
-    // disjoint column halves of the same one: any order is fine
-    for (int ci : o.convs) LEOD_TRY(conv_bwd_b(h, h->convs[ci], g, st));
+    LEOD_TRY(phase_bwd(h, o, g, st));
+  }
+  for (int i = 0; i < 2; ++i) {   // the weight-gradient streams join before the gradients are un-permuted / handed over
+    LEOD_CUDA(cudaEventRecord(h->ev_join[2 + i], h->wg_stream[i]));
+    LEOD_CUDA(cudaStreamWaitEvent(st, h->ev_join[2 + i], 0));
   }
   {
     dim3 grid(std::max(1, std::min(64, ceil_div(h->max_prep_items, 256))), h->n_prep);

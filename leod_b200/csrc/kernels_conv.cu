@@ -181,13 +181,59 @@ __global__ void col2im_pad_s2_kernel(const T *__restrict__ dcol, int ldcol, PadG
 }
 
 // ------------------------------------------------------------------ BatchNorm (+SiLU)
-// stats layout (double): [0, C) sum, [C, 2C) sum of squares, [2C] element count per channel.
+// Per convolution: `stats` (double) = [0, C) sum, [C, 2C) sum of squares, [2C] element count, [2C+1] block ticket;
+// `fin` (float) = [0, C) mean, [C, 2C) 1/sqrt(var + eps), written once per forward by the LAST block of the statistics
+// kernel (or by bn_finalize_kernel after the data-parallel exchange), so the apply kernels never touch fp64.
+// Backward likewise: `dstat` (double) = [0, C) sum dyhat, [C, 2C) sum dyhat*xhat, [2C] ticket; `dfin` (float) = the two means.
 constexpr int BN_THREADS = 256;
 
+struct BnFin {       // everything the finalisation needs
+  double *stats;     // forward sums (+ count) — global in data-parallel mode
+  float *fin;
+  BnSeg s0, s1;
+  int cseg;
+  float eps, momentum;
+  int update_running;
+};
+
+__device__ __forceinline__ void bn_finalize_channels(const BnFin &f, int C, int tid, int nthreads) {
+  const double n = f.stats[2 * C];
+  const double inv = 1.0 / n;
+  for (int c = tid; c < C; c += nthreads) {
+    const double m = f.stats[c] * inv;
+    const double v = fmax(f.stats[C + c] * inv - m * m, 0.0);
+    f.fin[c] = (float)m;
+    f.fin[C + c] = rsqrtf((float)v + f.eps);
+    if (f.update_running) {   // torch.nn.BatchNorm2d: momentum 0.1, unbiased variance (network_blocks.py:46)
+      const BnSeg &sg = c < f.cseg ? f.s0 : f.s1;
+      const int cl = c < f.cseg ? c : c - f.cseg;
+      if (sg.rmean) {
+        sg.rmean[cl] = (1.f - f.momentum) * sg.rmean[cl] + f.momentum * (float)m;
+        sg.rvar[cl] = (1.f - f.momentum) * sg.rvar[cl] + f.momentum * (float)(v * (n / fmax(n - 1.0, 1.0)));
+      }
+      if (cl == 0 && sg.nbt) sg.nbt[0] += 1;
+    }
+  }
+}
+// true in every thread of the last block to arrive (all other blocks' atomics are then visible)
+__device__ __forceinline__ bool last_block(double *ticket_slot) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long t = atomicAdd(reinterpret_cast<unsigned long long *>(ticket_slot), 1ULL);
+    s_last = (t == (unsigned long long)gridDim.x - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *__restrict__ Y, int ldy, PadGeom g, int C, double *__restrict__ stats,
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *__restrict__ Y, int ldy, PadGeom g, int C, BnFin f, int finalize,
                                                               int rows_per_block) {
   __shared__ float red[BN_THREADS][17];
+  double *stats = f.stats;
   const int nc = C >> 3;
   const int tid = threadIdx.x;
   const int rl = tid / nc, chunk = tid - rl * nc;
@@ -197,15 +243,23 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *__restric
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   const int64_t r1 = min(g.R, r0 + rows_per_block);
-  if (rl < lanes) {
-    for (int64_t r = r0 + rl; r < r1; r += lanes) {
+  for (int64_t rb = r0 + rl; rb < r1; rb += 4 * lanes) {   // four rows in flight per thread
+    V8 v[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = rb + (int64_t)u * lanes;
       int y, x;
-      if (!pad_pixel((int)(r % g.P), g, y, x)) continue;
-      const V8 v = load8<T>(Y + r * ldy + chunk * 8);
+      ok[u] = r < r1 && pad_pixel((int)(r % g.P), g, y, x);
+      if (ok[u]) v[u] = load8<T>(Y + r * ldy + chunk * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        s[j] += v.v[j];
-        ss[j] = fmaf(v.v[j], v.v[j], ss[j]);
+        s[j] += v[u].v[j];
+        ss[j] = fmaf(v[u].v[j], v[u].v[j], ss[j]);
       }
     }
   }
@@ -222,70 +276,82 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *__restric
     atomicAdd(&stats[(j >> 3) * C + c * 8 + (j & 7)], t);
   }
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&stats[2 * C], (double)g.B * g.h * g.w);
+  if (finalize && last_block(&stats[2 * C + 1])) bn_finalize_channels(f, C, tid, blockDim.x);
+}
+__global__ void __launch_bounds__(BN_THREADS) bn_finalize_kernel(BnFin f, int C) { bn_finalize_channels(f, C, threadIdx.x, blockDim.x); }
+
+// 8 consecutive floats as two 16-byte loads
+__device__ __forceinline__ V8 ldg8(const float *p) {
+  V8 r;
+  const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
 }
 
-// z = silu(gamma * (y - mean) * rstd + beta) on interior rows, 0 on the border.  training: batch statistics from `stats`
-// (+ running-statistics update, momentum 0.1, unbiased variance — torch.nn.BatchNorm2d defaults as built by
-// network_blocks.py:46); eval: the running statistics.  Two parameter segments serve the fused twin convolutions.
+// z = silu(gamma * (y - mean) * rstd + beta) on interior rows, 0 on the border.  training: batch statistics from `fin`;
+// eval: the running statistics.  Two parameter segments serve the fused twin convolutions.  One (row, 8-channel chunk) per
+// thread: these matrices are a few MB, so the kernel is a latency chain and wants every load in flight at once.
 template <typename T>
-__global__ void __launch_bounds__(BN_THREADS) bn_apply_silu_kernel(const T *__restrict__ Y, int ldy, PadGeom g, int C, const double *__restrict__ stats,
-                                                                   BnSeg s0, BnSeg s1, int cseg, T *__restrict__ Z, int ldz, float eps,
-                                                                   float momentum, int training, int rows_per_block) {
+__global__ void __launch_bounds__(BN_THREADS) bn_apply_silu_kernel(const T *__restrict__ Y, int ldy, PadGeom g, int C, const float *__restrict__ fin,
+                                                                   BnSeg s0, BnSeg s1, int cseg, T *__restrict__ Z, int ldz, float eps, int training) {
   const int nc = C >> 3;
-  const int tid = threadIdx.x;
-  const int rl = tid / nc, chunk = tid - rl * nc;
-  const int lanes = blockDim.x / nc;
-  if (rl >= lanes) return;
-  float scale[8], shift[8];
-  {
-    const int c0 = chunk * 8;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.R * nc) return;
+  const int64_t r = i / nc;
+  const int c0 = (int)(i - r * nc) * 8;
+  int y, x;
+  V8 o = zero8();
+  if (pad_pixel((int)(r % g.P), g, y, x)) {
+    const V8 v = load8<T>(Y + r * ldy + c0);
     const BnSeg &sg = c0 < cseg ? s0 : s1;
     const int cl = c0 < cseg ? c0 : c0 - cseg;
-    const double n = training ? stats[2 * C] : 1.0;
+    const V8 ga = ldg8(sg.gamma + cl), be = ldg8(sg.beta + cl);
+    const V8 mean = training ? ldg8(fin + c0) : ldg8(sg.rmean + cl);
+    V8 rstd;
+    if (training) {
+      rstd = ldg8(fin + C + c0);
+    } else {
+      rstd = ldg8(sg.rvar + cl);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rstd.v[j] = rsqrtf(rstd.v[j] + eps);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float mean, var;
-      if (training) {
-        const double m = stats[c0 + j] / n;
-        const double v = fmax(stats[C + c0 + j] / n - m * m, 0.0);
-        mean = (float)m;
-        var = (float)v;
-        if (blockIdx.x == 0 && rl == 0 && sg.rmean) {
-          sg.rmean[cl + j] = (1.f - momentum) * sg.rmean[cl + j] + momentum * mean;
-          sg.rvar[cl + j] = (1.f - momentum) * sg.rvar[cl + j] + momentum * (float)(v * (n / fmax(n - 1.0, 1.0)));
-        }
-      } else {
-        mean = sg.rmean[cl + j];
-        var = sg.rvar[cl + j];
-      }
-      const float rstd = rsqrtf(var + eps);
-      scale[j] = sg.gamma[cl + j] * rstd;
-      shift[j] = sg.beta[cl + j] - mean * scale[j];
+      const float sc = ga.v[j] * rstd.v[j];
+      const float u = fmaf(v.v[j] - mean.v[j], sc, be.v[j]);
+      o.v[j] = u / (1.f + __expf(-u));
     }
-    if (training && blockIdx.x == 0 && rl == 0 && sg.nbt && cl == 0) sg.nbt[0] += 1;
   }
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(g.R, r0 + rows_per_block);
-  for (int64_t r = r0 + rl; r < r1; r += lanes) {
-    int y, x;
-    V8 o = zero8();
-    if (pad_pixel((int)(r % g.P), g, y, x)) {
-      const V8 v = load8<T>(Y + r * ldy + chunk * 8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float u = fmaf(v.v[j], scale[j], shift[j]);
-        o.v[j] = u / (1.f + __expf(-u));
-      }
+  store8<T>(Z + r * ldz + c0, o);
+}
+
+struct BnBwdFin {
+  double *dloc, *dglob;   // local sums / sums over all ranks (the same array in a single process)
+  const double *stats;    // forward statistics (for the element count)
+  float *dfin;
+  BnSeg s0, s1;
+  int cseg;
+};
+// means over the (global) batch for the input gradient; dgamma += LOCAL sum dyhat*xhat, dbeta += LOCAL sum dyhat (SyncBatchNorm
+// semantics: the parameter gradients stay local, the data-parallel average happens in the flat-gradient all-reduce)
+__device__ __forceinline__ void bn_bwd_finalize_channels(const BnBwdFin &f, int C, int tid, int nthreads) {
+  const double inv = 1.0 / f.stats[2 * C];
+  for (int c = tid; c < C; c += nthreads) {
+    f.dfin[c] = (float)(f.dglob[c] * inv);
+    f.dfin[C + c] = (float)(f.dglob[C + c] * inv);
+    const BnSeg &sg = c < f.cseg ? f.s0 : f.s1;
+    const int cl = c < f.cseg ? c : c - f.cseg;
+    if (sg.dgamma) {
+      sg.dgamma[cl] += (float)f.dloc[C + c];
+      sg.dbeta[cl] += (float)f.dloc[c];
     }
-    store8<T>(Z + r * ldz + chunk * 8, o);
   }
 }
 
 // dyhat = dz * silu'(u);  dstat[0,C) += sum dyhat,  dstat[C,2C) += sum dyhat * xhat
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T *__restrict__ dZ, int lddz, const T *__restrict__ Y, int ldy, PadGeom g, int C,
-                                                                   const double *__restrict__ stats, BnSeg s0, BnSeg s1, int cseg, float eps,
-                                                                   double *__restrict__ dstat, int rows_per_block) {
+                                                                   const float *__restrict__ fin, BnBwdFin f, int finalize, int rows_per_block) {
   __shared__ float red[BN_THREADS][17];
   const int nc = C >> 3;
   const int tid = threadIdx.x;
@@ -294,36 +360,38 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T *__re
   float a1[8], a2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
-  if (rl < lanes) {
+  {
     const int c0 = chunk * 8;
-    const BnSeg &sg = c0 < cseg ? s0 : s1;
-    const int cl = c0 < cseg ? c0 : c0 - cseg;
-    float mean[8], rstd[8], ga[8], be[8];
-    const double n = stats[2 * C];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const double m = stats[c0 + j] / n;
-      const double v = fmax(stats[C + c0 + j] / n - m * m, 0.0);
-      mean[j] = (float)m;
-      rstd[j] = rsqrtf((float)v + eps);
-      ga[j] = sg.gamma[cl + j];
-      be[j] = sg.beta[cl + j];
-    }
+    const BnSeg &sg = c0 < f.cseg ? f.s0 : f.s1;
+    const int cl = c0 < f.cseg ? c0 : c0 - f.cseg;
+    const V8 mean = ldg8(fin + c0), rstd = ldg8(fin + C + c0), ga = ldg8(sg.gamma + cl), be = ldg8(sg.beta + cl);
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(g.R, r0 + rows_per_block);
-    for (int64_t r = r0 + rl; r < r1; r += lanes) {
-      int y, x;
-      if (!pad_pixel((int)(r % g.P), g, y, x)) continue;
-      const V8 yv = load8<T>(Y + r * ldy + c0);
-      const V8 dz = load8<T>(dZ + r * lddz + c0);
+    for (int64_t rb = r0 + rl; rb < r1; rb += 2 * lanes) {   // two rows (four loads) in flight per thread
+      V8 yv[2], dz[2];
+      bool ok[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (yv.v[j] - mean[j]) * rstd[j];
-        const float u = fmaf(ga[j], xh, be[j]);
-        const float sg_ = 1.f / (1.f + __expf(-u));
-        const float dyh = dz.v[j] * sg_ * (1.f + u * (1.f - sg_));
-        a1[j] += dyh;
-        a2[j] = fmaf(dyh, xh, a2[j]);
+      for (int u = 0; u < 2; ++u) {
+        const int64_t r = rb + (int64_t)u * lanes;
+        int y, x;
+        ok[u] = r < r1 && pad_pixel((int)(r % g.P), g, y, x);
+        if (ok[u]) {
+          yv[u] = load8<T>(Y + r * ldy + c0);
+          dz[u] = load8<T>(dZ + r * lddz + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (yv[u].v[j] - mean.v[j]) * rstd.v[j];
+          const float uu = fmaf(ga.v[j], xh, be.v[j]);
+          const float sg_ = 1.f / (1.f + __expf(-uu));
+          const float dyh = dz[u].v[j] * sg_ * (1.f + uu * (1.f - sg_));
+          a1[j] += dyh;
+          a2[j] = fmaf(dyh, xh, a2[j]);
+        }
       }
     }
   }
@@ -337,61 +405,41 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T *__re
     const int c = i >> 4, j = i & 15;
     double t = 0.0;
     for (int l = 0; l < lanes; ++l) t += (double)red[l * nc + c][j];
-    atomicAdd(&dstat[(j >> 3) * C + c * 8 + (j & 7)], t);
+    atomicAdd(&f.dloc[(j >> 3) * C + c * 8 + (j & 7)], t);
   }
+  if (finalize && last_block(&f.dloc[2 * C])) bn_bwd_finalize_channels(f, C, tid, blockDim.x);
 }
-// dy = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat)) with the means over the (global) batch;
-// dgamma += local sum dyhat*xhat, dbeta += local sum dyhat (SyncBatchNorm semantics: the parameter gradients stay local,
-// the data-parallel average happens in the flat-gradient all-reduce).
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_finalize_kernel(BnBwdFin f, int C) { bn_bwd_finalize_channels(f, C, threadIdx.x, blockDim.x); }
+
+// dy = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat)), 0 on the border
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T *__restrict__ dZ, int lddz, const T *__restrict__ Y, int ldy, PadGeom g, int C,
-                                                                  const double *__restrict__ stats, const double *__restrict__ dstat_global,
-                                                                  const double *__restrict__ dstat_local, BnSeg s0, BnSeg s1, int cseg, float eps,
-                                                                  T *__restrict__ dY, int lddy, int rows_per_block) {
+                                                                  const float *__restrict__ fin, const float *__restrict__ dfin, BnSeg s0, BnSeg s1,
+                                                                  int cseg, T *__restrict__ dY, int lddy) {
   const int nc = C >> 3;
-  const int tid = threadIdx.x;
-  const int rl = tid / nc, chunk = tid - rl * nc;
-  const int lanes = blockDim.x / nc;
-  if (rl >= lanes) return;
-  const int c0 = chunk * 8;
-  const BnSeg &sg = c0 < cseg ? s0 : s1;
-  const int cl = c0 < cseg ? c0 : c0 - cseg;
-  float mean[8], rstd[8], ga[8], be[8], m1[8], m2[8];
-  const double n = stats[2 * C];
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.R * nc) return;
+  const int64_t r = i / nc;
+  const int c0 = (int)(i - r * nc) * 8;
+  int y, x;
+  V8 o = zero8();
+  if (pad_pixel((int)(r % g.P), g, y, x)) {
+    const V8 yv = load8<T>(Y + r * ldy + c0);
+    const V8 dz = load8<T>(dZ + r * lddz + c0);
+    const BnSeg &sg = c0 < cseg ? s0 : s1;
+    const int cl = c0 < cseg ? c0 : c0 - cseg;
+    const V8 ga = ldg8(sg.gamma + cl), be = ldg8(sg.beta + cl), mean = ldg8(fin + c0), rstd = ldg8(fin + C + c0), m1 = ldg8(dfin + c0),
+             m2 = ldg8(dfin + C + c0);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const double m = stats[c0 + j] / n;
-    const double v = fmax(stats[C + c0 + j] / n - m * m, 0.0);
-    mean[j] = (float)m;
-    rstd[j] = rsqrtf((float)v + eps);
-    ga[j] = sg.gamma[cl + j];
-    be[j] = sg.beta[cl + j];
-    m1[j] = (float)(dstat_global[c0 + j] / n);
-    m2[j] = (float)(dstat_global[C + c0 + j] / n);
-    if (blockIdx.x == 0 && rl == 0 && sg.dgamma) {
-      sg.dgamma[cl + j] += (float)dstat_local[C + c0 + j];
-      sg.dbeta[cl + j] += (float)dstat_local[c0 + j];
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (yv.v[j] - mean.v[j]) * rstd.v[j];
+      const float u = fmaf(ga.v[j], xh, be.v[j]);
+      const float sg_ = 1.f / (1.f + __expf(-u));
+      const float dyh = dz.v[j] * sg_ * (1.f + u * (1.f - sg_));
+      o.v[j] = ga.v[j] * rstd.v[j] * (dyh - m1.v[j] - xh * m2.v[j]);
     }
   }
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(g.R, r0 + rows_per_block);
-  for (int64_t r = r0 + rl; r < r1; r += lanes) {
-    int y, x;
-    V8 o = zero8();
-    if (pad_pixel((int)(r % g.P), g, y, x)) {
-      const V8 yv = load8<T>(Y + r * ldy + c0);
-      const V8 dz = load8<T>(dZ + r * lddz + c0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (yv.v[j] - mean[j]) * rstd[j];
-        const float u = fmaf(ga[j], xh, be[j]);
-        const float sg_ = 1.f / (1.f + __expf(-u));
-        const float dyh = dz.v[j] * sg_ * (1.f + u * (1.f - sg_));
-        o.v[j] = ga[j] * rstd[j] * (dyh - m1[j] - xh * m2[j]);
-      }
-    }
-    store8<T>(dY + r * lddy + c0, o);
-  }
+  store8<T>(dY + r * lddy + c0, o);
 }
 
 template <typename T> __global__ void fill_zero_kernel(T *p, int64_t n) {
@@ -476,40 +524,47 @@ int col2im_pad_s2(int dtype, const void *dcol, int ldcol, const PadGeom &go, voi
   return 0;
 }
 
-int bn_stats(int dtype, const void *Y, int ldy, const PadGeom &g, int C, double *stats, cudaStream_t st) {
-  LEOD_REQUIRE(C % 8 == 0 && C <= 8 * BN_THREADS, "bn_stats: C = %d", C);
+// finalize != 0: the last block also turns the sums into mean / rstd (single process); 0: bn_finalize() does it after the exchange
+int bn_stats(int dtype, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, int finalize, cudaStream_t st) {
+  LEOD_REQUIRE(l.C % 8 == 0 && l.cseg % 8 == 0 && l.C <= 8 * BN_THREADS, "bn_stats: C = %d", l.C);
   int threads, rpb, blocks;
-  bn_launch_shape(C, g.R, &threads, &rpb, &blocks);
-  DISPATCH_T(dtype, (bn_stats_kernel<T><<<blocks, threads, 0, st>>>((const T *)Y, ldy, g, C, stats, rpb)));
+  bn_launch_shape(l.C, g.R, &threads, &rpb, &blocks);
+  BnFin f{l.stats, l.fin, l.s0, l.s1, l.cseg, l.eps, l.momentum, 1};
+  DISPATCH_T(dtype, (bn_stats_kernel<T><<<blocks, threads, 0, st>>>((const T *)Y, ldy, g, l.C, f, finalize, rpb)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
-int bn_apply_silu(int dtype, const void *Y, int ldy, const PadGeom &g, int C, const double *stats, const BnSeg &s0, const BnSeg &s1, int cseg,
-                  void *Z, int ldz, float eps, float momentum, int training, cudaStream_t st) {
-  LEOD_REQUIRE(C % 8 == 0 && cseg % 8 == 0 && C <= 8 * BN_THREADS, "bn_apply_silu: C = %d", C);
-  int threads, rpb, blocks;
-  bn_launch_shape(C, g.R, &threads, &rpb, &blocks);
-  DISPATCH_T(dtype, (bn_apply_silu_kernel<T><<<blocks, threads, 0, st>>>((const T *)Y, ldy, g, C, stats, s0, s1, cseg, (T *)Z, ldz, eps, momentum,
-                                                                         training, rpb)));
+int bn_finalize(const BnLayer &l, cudaStream_t st) {
+  BnFin f{l.stats, l.fin, l.s0, l.s1, l.cseg, l.eps, l.momentum, 1};
+  bn_finalize_kernel<<<1, BN_THREADS, 0, st>>>(f, l.C);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
-int bn_bwd_reduce(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, int C, const double *stats, const BnSeg &s0,
-                  const BnSeg &s1, int cseg, float eps, double *dstat, cudaStream_t st) {
-  int threads, rpb, blocks;
-  bn_launch_shape(C, g.R, &threads, &rpb, &blocks);
-  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<blocks, threads, 0, st>>>((const T *)dZ, lddz, (const T *)Y, ldy, g, C, stats, s0, s1, cseg, eps, dstat,
-                                                                         rpb)));
+int bn_apply_silu(int dtype, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, void *Z, int ldz, int training, cudaStream_t st) {
+  const int blocks = ceil_div(g.R * (l.C / 8), BN_THREADS);
+  DISPATCH_T(dtype, (bn_apply_silu_kernel<T><<<blocks, BN_THREADS, 0, st>>>((const T *)Y, ldy, g, l.C, l.fin, l.s0, l.s1, l.cseg, (T *)Z, ldz, l.eps,
+                                                                            training)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
-int bn_bwd_apply(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, int C, const double *stats,
-                 const double *dstat_global, const double *dstat_local, const BnSeg &s0, const BnSeg &s1, int cseg, float eps, void *dY, int lddy,
-                 cudaStream_t st) {
+int bn_bwd_reduce(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, int finalize, cudaStream_t st) {
   int threads, rpb, blocks;
-  bn_launch_shape(C, g.R, &threads, &rpb, &blocks);
-  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<blocks, threads, 0, st>>>((const T *)dZ, lddz, (const T *)Y, ldy, g, C, stats, dstat_global, dstat_local,
-                                                                        s0, s1, cseg, eps, (T *)dY, lddy, rpb)));
+  bn_launch_shape(l.C, g.R, &threads, &rpb, &blocks);
+  BnBwdFin f{l.dloc, l.dglob, l.stats, l.dfin, l.s0, l.s1, l.cseg};
+  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<blocks, threads, 0, st>>>((const T *)dZ, lddz, (const T *)Y, ldy, g, l.C, l.fin, f, finalize, rpb)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+int bn_bwd_finalize(const BnLayer &l, cudaStream_t st) {
+  BnBwdFin f{l.dloc, l.dglob, l.stats, l.dfin, l.s0, l.s1, l.cseg};
+  bn_bwd_finalize_kernel<<<1, BN_THREADS, 0, st>>>(f, l.C);
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+int bn_bwd_apply(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, void *dY, int lddy, cudaStream_t st) {
+  const int blocks = ceil_div(g.R * (l.C / 8), BN_THREADS);
+  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<blocks, BN_THREADS, 0, st>>>((const T *)dZ, lddz, (const T *)Y, ldy, g, l.C, l.fin, l.dfin, l.s0, l.s1,
+                                                                           l.cseg, (T *)dY, lddy)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }

@@ -552,6 +552,21 @@ int pick_bn(int M, int N, int K) {
   const int cap = 256;
   (void)K;
   const int tiles_m = ceil_div(M, TILE_M);
+  if (tiles_m < 2 * 148) {
+    // Small problems (the neck / head layers, the late backbone stages): a handful of waves at most, so what matters is how
+    // many SMs take part and how long the longest CTA runs.  Cost model: waves x (tile width + a fixed per-tile share for the
+    // A tile, pipeline fill and epilogue start-up, about 64 columns' worth).
+    int best = 0;
+    long best_cost = 0;
+    for (int bn = cap; bn >= 16; bn -= 16) {
+      if (N % bn != 0 && !(N <= bn && bn == (int)round_up(N, 16))) continue;
+      const long waves = ceil_div((long)tiles_m * ceil_div(N, bn), 148);
+      const long cost = waves * (bn + 64);
+      if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+    }
+    if (best) return best;
+    return N <= cap ? (int)round_up(N, 16) : 256;
+  }
   int best = 0;
   for (int bn = cap; bn >= 32; bn -= 16) {
     if (N % bn != 0 && !(N <= bn && bn == (int)round_up(N, 16))) continue;
@@ -1533,8 +1548,12 @@ int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int l
   // each split ends in an atomic epilogue over the whole output tile, so splits are only worth it when
   // they still stream a few thousand rows each; small-M problems run unsplit (plain read-modify-write)
   a.tiles_k = tk;
-  int splits = ceil_div(148, tn * tk * ntap);
-  const int max_splits = M <= 4096 ? 1 : ceil_div(M, 2048);
+  // Backbone shapes (M up to 860k rows): each split ends in an atomic epilogue, so it should stream a few thousand rows.
+  // The tapped / small-M problems of the neck and head are latency chains of 64-row k-blocks instead: split them finely enough
+  // that ~2 waves of CTAs share the reduction.
+  const bool fine = taps != nullptr || M <= 32768;
+  int splits = ceil_div(fine ? 2 * 148 : 148, tn * tk * ntap);
+  const int max_splits = fine ? std::max(1, M / 256) : (M <= 4096 ? 1 : ceil_div(M, 2048));
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   a.rows_per_split = (int)round_up(ceil_div(M, splits), 64);

