@@ -76,6 +76,12 @@ class SparselyBatchedObjectLabels:
     def is_empty(self):
         return all(l is None for l in self.sparse_object_labels_batch)
 
+    def set_non_gt_labels_to_none_(self) -> None:
+        """data/genx_utils/labels.py:645-648: drop frames that carry pseudo labels only (t == 0 in every row)."""
+        for i, l in enumerate(self.sparse_object_labels_batch):
+            if l is not None and bool((l.object_labels[:, 0] == 0).all()):
+                self.sparse_object_labels_batch[i] = None
+
     def flip_lr_(self) -> None:
         for l in self.sparse_object_labels_batch:
             if l is not None:
@@ -85,11 +91,14 @@ class SparselyBatchedObjectLabels:
         return SparselyBatchedObjectLabels([None if l is None else l.clone() for l in self.sparse_object_labels_batch])
 
     def get_valid_labels_and_batch_indices(self, ignore: bool = False, ignore_label: int = 1024):
-        """labels.py:~700-730: entries that carry at least one box (optionally skipping frames whose
-        boxes are all `ignore_label`)."""
+        """data/genx_utils/labels.py:716-729: every non-None entry — INCLUDING labels with zero boxes (frames emptied by the
+        zoom/crop augmentation train as background-only frames) — optionally skipping frames whose boxes all carry
+        `ignore_label` (an empty label counts as all-ignore there too, `.all()` of nothing)."""
+        if ignore:
+            assert ignore_label is not None, 'ignore_label must be provided'
         labels, idx = [], []
         for i, l in enumerate(self.sparse_object_labels_batch):
-            if l is None or len(l) == 0:
+            if l is None:
                 continue
             if ignore and bool((l.object_labels[:, 5] == ignore_label).all()):
                 continue

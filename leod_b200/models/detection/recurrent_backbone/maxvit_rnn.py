@@ -74,12 +74,17 @@ class _BackboneSeq(torch.autograd.Function):
         outs, keep = bb._seq_forward(x, states)
         ctx.bb = bb
         ctx.keep = keep
+        ctx.gen = bb._seq_gen
         ctx.state_mask = [s is not None for s in states]
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(*outs[:4])
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *grads):
+        if ctx.gen != ctx.bb._seq_gen:
+            raise RuntimeError('leod_b200 backbone: another forward_sequence ran between this forward and its backward; the library '
+                               'keeps the activations of ONE window (leod_backbone_seq_arena_bytes) — run backward first')
         dstates = ctx.bb._seq_backward(ctx.keep, ctx.saved_tensors, grads)
         ctx.keep = None
         return (None, None, None) + tuple(d if m else None for d, m in zip(dstates, ctx.state_mask))
@@ -136,6 +141,7 @@ class RNNDetector(nn.Module):
         self._anchor = None
         self._prepared_version = None
         self._bwd_pending = False
+        self._seq_gen = 0              # forward_sequence calls so far: a backward must belong to the latest one (shared arena)
         self.grad_sync = None          # optional callable(flat_grad) -> None, e.g. an all-reduce
         self._register_params()
         self.reset_parameters()
@@ -389,6 +395,7 @@ class RNNDetector(nn.Module):
         L, B = x.shape[0], x.shape[1]
         dev = x.device
         shapes = self._state_shapes(B)
+        self._seq_gen += 1
         if x.dtype not in (torch.float32, torch.bfloat16, torch.uint8):
             x = x.float()
         x = x.contiguous()

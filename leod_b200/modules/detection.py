@@ -67,9 +67,18 @@ class Module(_Base):
 
     # ------------------------------------------------------------------ data
     def get_data_from_batch(self, batch: Any):
-        """modules/detection.py:129-148.  The uint8 -> float cast and the zero padding to
-        `in_res_hw` are fused into the stem's patch loader, so tensors pass through untouched."""
-        return batch[DATA_KEY]
+        """modules/detection.py:129-148.  The uint8 -> float cast and the zero padding to `in_res_hw` are fused into the
+        stem's patch loader, so the event tensors pass through untouched.  In training the label sub-sampling of :137-147
+        (`model.use_label_every`) is applied: timesteps outside `label_subsample_idx` keep ground truth only."""
+        data = batch[DATA_KEY]
+        if not self.training:
+            return data
+        sparse_obj_labels = dget(data, DataType.OBJLABELS_SEQ)
+        if len(self.label_subsample_idx) < len(sparse_obj_labels):
+            for tidx in range(len(sparse_obj_labels)):
+                if tidx not in self.label_subsample_idx:
+                    sparse_obj_labels[tidx].set_non_gt_labels_to_none_()
+        return data
 
     # ------------------------------------------------------------------ train
     def training_step(self, batch: Any, batch_idx: int = 0, log: bool = False):
@@ -213,7 +222,7 @@ class FlatOptimizer:
     kernel launch per buffer per step (leod_adamw_ema) instead of ~4 launches x 376 tensors."""
 
     def __init__(self, detector: YoloXDetector, lr: float, weight_decay: float = 0.0, clip_value: float = 1.0,
-                 betas=(0.9, 0.999), eps: float = 1e-8, ema: bool = False, ema_alpha: float = 0.999):
+                 betas=(0.9, 0.999), eps: float = 1e-8, ema: bool = False, ema_alpha: float = 0.999, ema_buffers=None):
         self.detector = detector
         self.lr, self.wd, self.clip, self.betas, self.eps = lr, weight_decay, clip_value, betas, eps
         self.step_count = 0
@@ -223,7 +232,12 @@ class FlatOptimizer:
         self.bufs = [(bb.flat_params, bb.flat_grads), (de.flat_params, de.flat_grads)]
         self.m = [torch.zeros_like(p) for p, _ in self.bufs]
         self.v = [torch.zeros_like(p) for p, _ in self.bufs]
-        self.ema = [p.clone() for p, _ in self.bufs] if ema else [None, None]
+        # teacher EMA in the same launch: into private clones, or straight into a teacher model's flat parameter buffers
+        if ema_buffers is not None:
+            assert len(ema_buffers) == 2 and all(e.shape == p.shape and e.device == p.device for e, (p, _) in zip(ema_buffers, self.bufs))
+            self.ema = list(ema_buffers)
+        else:
+            self.ema = [p.clone() for p, _ in self.bufs] if ema else [None, None]
 
     def zero_grad(self):
         for _, g in self.bufs:

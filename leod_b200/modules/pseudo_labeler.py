@@ -135,7 +135,9 @@ class PseudoLabeler(Module):
                 has_skipped = skipped is not None and skipped[t][b] is not None
                 assert not (has_gt and has_skipped)
                 gt_mask[t, b] = has_gt
-                skip_mask[t, b] = has_gt or skip_mask[t, b]
+                # the reference OVERWRITES the mask here (pseudo_labeler.py:538), which voids step 1: the first frame(s) of a
+                # new sequence are predicted too.  Reproduced as is — the label sets must be identical.
+                skip_mask[t, b] = has_gt
                 skipped_gt_mask[t, b] = has_skipped
         if 'IS_PADDED_MASK' in data:
             padded = th.stack(list(data['IS_PADDED_MASK'])).cpu().numpy().astype(bool)

@@ -83,6 +83,26 @@ def ema_model_update(params: Sequence[torch.Tensor], ema_params: Sequence[torch.
 
 
 @torch.no_grad()
+def model_update(student_model: torch.nn.Module, teacher_model: torch.nn.Module, global_step: int, method: str = 'ema', alpha: float = 0.999):
+    """ssod.py:441-460: 'ema' -> ema_model_update over the parameters; 'every-N' -> hard copy of the student's state_dict
+    (parameters AND buffers) into the teacher whenever (global_step + 1) % N == 0."""
+    method = method.lower()
+    if method == 'ema':
+        ema_model_update([p.data for p in student_model.parameters()], [p.data for p in teacher_model.parameters()], global_step, alpha)
+    elif 'every-' in method:
+        num_step = int(method.split('-')[-1])
+        if (global_step + 1) % num_step == 0:
+            teacher_model.load_state_dict(student_model.state_dict())
+    else:
+        raise NotImplementedError(f'Unknown model update method: {method}')
+    for m in teacher_model.modules():       # the library keeps operand-typed weight copies: refresh them before the next forward
+        if hasattr(m, 'mark_params_updated'):
+            m.mark_params_updated()
+    if hasattr(teacher_model, 'detect_engine'):
+        teacher_model.detect_engine.mark_params_updated()
+
+
+@torch.no_grad()
 def fused_adamw_ema(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, clip_value=0.0,
                     ema: Optional[torch.Tensor] = None, ema_alpha: float = 0.999):
     """One launch over flat fp32 buffers: clip-by-value, AdamW, optional teacher EMA."""

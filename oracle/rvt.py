@@ -123,3 +123,84 @@ def pad_input(ev: torch.Tensor, hw: Tuple[int, int]) -> torch.Tensor:
     """utils/padding.py:33-58 + modules/detection.py:132: cast to float, zero-pad bottom/right."""
     H, W = ev.shape[-2:]
     return F.pad(ev.float(), (0, hw[1] - W, 0, hw[0] - H))
+
+
+def init_state_dict(cfg: ModelCfg, input_channels: int = 20, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """A state_dict with the reference's parameter names / shapes and its constructors' distributions (nn.Conv2d / nn.Linear default
+    init, LayerNorm and BatchNorm (1, 0), LayerScale 1e-5 — maxvit.py:45-53 —, prior-probability head biases — yolo_head.py:183-193),
+    for the oracle-port arm of bench.py when oracle/_ref is absent.  Shapes: maxvit_rnn.py:23-95, maxvit.py:143-182, 185-354,
+    models/layers/rnn.py:7-36, yolo_pafpn.py:18-107, network_blocks.py:29-142, yolo_head.py:21-182."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def uni(shape, fan_in):
+        b = 1.0 / math.sqrt(fan_in)
+        return (torch.rand(shape, generator=g) * 2 - 1) * b
+
+    def linear(p, cout, cin, bias=True):
+        sd[p + '.weight'] = uni((cout, cin), cin)
+        if bias:
+            sd[p + '.bias'] = uni((cout,), cin)
+
+    def norm(p, c):
+        sd[p + '.weight'], sd[p + '.bias'] = torch.ones(c), torch.zeros(c)
+
+    dims = cfg.stage_dims
+    cin = input_channels
+    for si, c in enumerate(dims):
+        p = f'backbone.stages.{si}'
+        k = 7 if si == 0 else 3
+        sd[p + '.downsample_cf2cl.conv.weight'] = uni((c, cin, k, k), cin * k * k)
+        norm(p + '.downsample_cf2cl.norm', c)
+        for bi, blk in enumerate(('att_window', 'att_grid')):
+            q = f'{p}.att_blocks.0.{blk}'
+            if bi > 0:
+                norm(q + '.norm1', c)
+            linear(q + '.self_attn.qkv', 3 * c, c)
+            linear(q + '.self_attn.proj', c, c)
+            sd[q + '.ls1.gamma'] = torch.full((c,), 1e-5)
+            norm(q + '.norm2', c)
+            linear(q + '.mlp.net.0.0', cfg.mlp_ratio * c, c)
+            linear(q + '.mlp.net.2', c, cfg.mlp_ratio * c)
+            sd[q + '.ls2.gamma'] = torch.full((c,), 1e-5)
+        sd[p + '.lstm.conv1x1.weight'] = uni((4 * c, 2 * c, 1, 1), 2 * c)
+        sd[p + '.lstm.conv1x1.bias'] = uni((4 * c,), 2 * c)
+        cin = c
+
+    def cbs(p, co, ci, k):
+        sd[p + '.conv.weight'] = uni((co, ci, k, k), ci * k * k)
+        sd[p + '.bn.weight'], sd[p + '.bn.bias'] = torch.ones(co), torch.zeros(co)
+        sd[p + '.bn.running_mean'], sd[p + '.bn.running_var'] = torch.zeros(co), torch.ones(co)
+        sd[p + '.bn.num_batches_tracked'] = torch.zeros((), dtype=torch.long)
+
+    def csp(p, ci, co, n):
+        h = co // 2
+        cbs(p + '.conv1', h, ci, 1)
+        cbs(p + '.conv2', h, ci, 1)
+        cbs(p + '.conv3', co, 2 * h, 1)
+        for i in range(n):
+            cbs(f'{p}.m.{i}.conv1', h, h, 1)
+            cbs(f'{p}.m.{i}.conv2', h, h, 3)
+
+    c0, c1, c2 = (dims[s - 1] for s in cfg.in_stages)
+    n = round(3 * cfg.fpn_depth)
+    cbs('fpn.lateral_conv0', c1, c2, 1)
+    csp('fpn.C3_p4', 2 * c1, c1, n)
+    cbs('fpn.reduce_conv1', c0, c1, 1)
+    csp('fpn.C3_p3', 2 * c0, c0, n)
+    cbs('fpn.bu_conv2', c0, c0, 3)
+    csp('fpn.C3_n3', 2 * c0, c1, n)
+    cbs('fpn.bu_conv1', c1, c1, 3)
+    csp('fpn.C3_n4', 2 * c1, c2, n)
+    hid = int(256 * c2 / 1024)
+    prior = -math.log((1 - 0.01) / 0.01)
+    for k, c in enumerate((c0, c1, c2)):
+        cbs(f'yolox_head.stems.{k}', hid, c, 1)
+        for tower in ('cls_convs', 'reg_convs'):
+            cbs(f'yolox_head.{tower}.{k}.0', hid, hid, 3)
+            cbs(f'yolox_head.{tower}.{k}.1', hid, hid, 3)
+        for name, co in (('cls_preds', cfg.num_classes), ('reg_preds', 4), ('obj_preds', 1)):
+            sd[f'yolox_head.{name}.{k}.weight'] = uni((co, hid, 1, 1), hid)
+            sd[f'yolox_head.{name}.{k}.bias'] = uni((co,), hid) if name == 'reg_preds' else torch.full((co,), prior)
+    return sd

@@ -229,7 +229,7 @@ def test_backward_smooth_loss_matches_oracle(case, dtype, weights):
         errs.append(err)
         worst = max(worst, (err, name))
         assert err < gtol, (name, err)
-    assert fp32 or sorted(errs)[len(errs) // 2] < 4e-2
+    assert fp32 or sorted(errs)[len(errs) // 2] < (4e-2 if weights == 'init' else 6e-2)
     for s, d in zip(cfg.in_stages, dfe):
         err = rel_err(d.float().cpu(), rf[s].grad)
         worst = max(worst, (err, f'feat{s}'))

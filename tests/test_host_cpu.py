@@ -141,11 +141,35 @@ def test_pseudo_labeler_masks_and_hflip_batch_doubling(net):
     pl.mode_2_seq_lens.lens[0] = torch.tensor([0, 5, 0, 5])
     pse, gt, skipped_gt = pl._get_pred_mask(worker_id=0, data=out)
     exp = np.ones((L, 2 * B), bool)
-    exp[:2, 0] = exp[:2, 2] = False           # skip_first_t
+    # the reference overwrites the skip_first_t rows in its GT loop (modules/pseudo_labeler.py:538 `skip_mask[tidx, bidx] = has_gt`),
+    # so the first frames of a fresh sequence ARE predicted: only padding and ground truth switch a frame off
     exp[2, 0] = exp[2, 2] = False             # padded
     exp[3, 1] = exp[3, 3] = False             # ground truth present
     np.testing.assert_array_equal(pse, exp)
     assert gt.sum() == 2 and gt[3, 1] and gt[3, 3] and skipped_gt.sum() == 0
+
+
+def test_model_update_modes():
+    """modules/utils/ssod.py:429-460: EMA with the true-average warm-up, and the 'every-N' hard copy (parameters and buffers)."""
+    from leod_b200.modules.utils.ssod import ema_alpha_at, model_update
+    torch.manual_seed(0)
+    student = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))
+    teacher = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))
+    s0 = [p.detach().clone() for p in student.parameters()]
+    t0 = [p.detach().clone() for p in teacher.parameters()]
+    assert ema_alpha_at(0) == 0.0 and ema_alpha_at(1) == 0.5 and ema_alpha_at(10 ** 6) == 0.999
+    model_update(student, teacher, global_step=1, method='ema')
+    for t, a, b in zip(teacher.parameters(), t0, s0):
+        assert rel_err(t, 0.5 * a + 0.5 * b) < 1e-6
+    student[1].running_mean.fill_(3.0)
+    model_update(student, teacher, global_step=0, method='every-2')       # (0 + 1) % 2 != 0: untouched
+    assert float(teacher[1].running_mean.abs().max()) == 0.0
+    model_update(student, teacher, global_step=1, method='every-2')
+    assert float(teacher[1].running_mean.min()) == 3.0
+    for t, b in zip(teacher.parameters(), s0):
+        assert rel_err(t, b) == 0.0
+    with pytest.raises(NotImplementedError):
+        model_update(student, teacher, 0, method='nope')
 
 
 def test_bench_reference_arm_prints_the_contract_line():
@@ -161,7 +185,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['unit'] == 'event-frames/s' and d['higher_is_better'] is True
     assert d['value'] > 0 and d['steps'] == 1 and d['n_gpus'] == 1 and d['vs_baseline'] is None
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'event-frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']
 
