@@ -172,6 +172,32 @@ class Module(_Base):
                                      conf_thre=pp.confidence_threshold, nms_thre=pp.nms_threshold)
         return {'labels': obj_labels, 'predictions': pred_processed, 'skip': False}
 
+    @torch.inference_mode()
+    def predict_one_seq(self, batch: Any, chunk: int = 128):
+        """modules/detection.py:520-581: run the model over ONE full event sequence (batch size 1) and return
+        (per-timestep detections `L`-len list of [N_t, 7] | None, the event tensors [L, C, H, W], the `L`-len label list).
+        The time loop runs in the library `chunk` timesteps at a time (the reference batches the head over 128 timesteps, :545)."""
+        mode = Mode.TEST
+        data = self.get_data_from_batch(batch)
+        worker_id = batch[WORKER_ID_KEY]
+        ev_seq = dget(data, DataType.EV_REPR)
+        ev = (ev_seq if torch.is_tensor(ev_seq) else torch.stack(list(ev_seq), dim=0)).cuda()
+        sparse_obj_labels = dget(data, DataType.OBJLABELS_SEQ)
+        is_first_sample = dget(data, DataType.IS_FIRST_SAMPLE)
+        assert ev.shape[1] == len(sparse_obj_labels[0]) == is_first_sample.shape[0] == 1
+        self.mode_2_rnn_states[mode].reset(worker_id=worker_id, indices_or_bool_tensor=is_first_sample)
+        L = ev.shape[0]
+        assert L > 0
+        pp = self.mdl_config.postprocess
+        prev_states, all_preds = None, []       # like the reference, the sequence starts from a zero state (:543)
+        for t0 in range(0, L, chunk):
+            feats_all, prev_states = self.mdl.backbone.forward_sequence(ev[t0:t0 + chunk], prev_states)
+            sel = {k: v[:, 0] for k, v in feats_all.items() if k in self.mdl.fpn.in_features}
+            predictions, _ = self.mdl.forward_detect(backbone_features=sel)
+            all_preds.extend(postprocess(prediction=predictions, num_classes=self.num_classes, conf_thre=pp.confidence_threshold,
+                                         nms_thre=pp.nms_threshold))
+        return all_preds, ev[:, 0], [lbl[0] for lbl in sparse_obj_labels]
+
     def validation_step(self, batch, batch_idx=0):
         return self._val_test_step_impl(batch, Mode.VAL)
 
