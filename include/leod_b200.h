@@ -256,6 +256,31 @@ int leod_pred2label(const float *dets, const int32_t *count, int B, int max_det,
 int leod_tta_merge(const float *labels, const int32_t *count, int F, int nmax, float conf_thre, float nms_thre,
                    int class_agnostic, float *out, int32_t *out_count, void *stream);
 
+/* ------------------------------------------------------------------ pseudo-label sequence post-processing
+ * Replaces EventSeqData._track / _track_filter (modules/pseudo_labeler.py:201-333) with modules/tracking/linear.py:10-292 and
+ * modules/tracking/utils.py:7-96 behind it, for S sequences in one call (one CTA per sequence and direction), bit-exact.
+ *  rows       : device fp32 [total_rows, 8] ObjectLabels rows (t, x, y, w, h, cls, cls_conf, obj) of every labelled frame, sequence after
+ *               sequence, frames ascending;  frame_ptr: device int32 [total_frames + 1] first row of each labelled frame;  frame_idx:
+ *               device int32 [total_frames] index of the frame inside its sequence;  seq_ptr: device int32 [S + 1] first labelled frame of
+ *               each sequence;  hw: device int32 [S, 2] frame height / width
+ *  qpow_host  : HOST doubles q^0 .. q^(npow-1) (npow > longest run of frames a track can age); q 0.9, min_conf 0.55, iou_thr 0.45,
+ *               min_track_len 6 are the reference's defaults (linear.py:200-206, config/predict.yaml)
+ *  use_backward : 'forward or backward' track_method — a box is ignored only if both directions put it on a short track
+ *  hole_cap   : capacity for in-painted boxes per sequence;  ws: device scratch of leod_track_workspace_bytes()
+ *  outputs    : out_rows + 8 * out_row_base[s] (capacity rows of s + hole_cap): the final rows, frame after frame, short-track boxes
+ *               and in-painted boxes carrying ignore_label;  out_frame_idx / out_frame_start + out_frame_base[s]: frame index and first
+ *               row of each output frame;  out_counts [S, 2] = rows, frames;  status [S]: 0 ok, 1 more than 64 live tracks or boxes per
+ *               frame, 2 hole_cap exceeded, 3 qpow too short. */
+int64_t leod_track_workspace_bytes(int64_t total_rows, int S, int hole_cap, int npow);
+int leod_track_filter(const float *rows, const int32_t *frame_ptr, const int32_t *frame_idx, const int32_t *seq_ptr, const int32_t *hw,
+                      int64_t total_rows, int total_frames, int S, const double *qpow_host, int npow, double q, double min_conf, float iou_thr,
+                      int min_track_len, int inpaint, int use_backward, float ignore_label, int hole_cap, void *ws,
+                      const int32_t *out_row_base, const int32_t *out_frame_base, float *out_rows, int32_t *out_frame_idx,
+                      int32_t *out_frame_start, int32_t *out_counts, int32_t *status, void *stream);
+/* ObjectLabels rows -> label-file records (data/genx_utils/labels.py:12-16 BBOX_DTYPE, :312-325 to_structured_array).
+ * stride 40 = the declared dtype, 36 = the packed form EventSeqData._summarize (modules/pseudo_labeler.py:179-199) stores. */
+int leod_pack_bbox(const float *rows, int64_t n, void *out, int stride, void *stream);
+
 /* ------------------------------------------------------------------ event binning
  * Replaces data/utils/representations.py:78-123 (StackedHistogram.construct).
  * x,y,p: device int32 [n]; t: device int64 [n] (sorted); out: device uint8 [2*bins, H, W].

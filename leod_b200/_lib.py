@@ -95,6 +95,10 @@ def _declare(lib):
         'leod_postprocess': (I, [VP, I, I, I, F, F, I, VP, VP, I, VP]),
         'leod_pred2label': (I, [VP, VP, I, I, I, POINTER(c_float), POINTER(c_float), I, I, VP, VP, VP]),
         'leod_tta_merge': (I, [VP, VP, I, I, F, F, I, VP, VP, VP]),
+        'leod_track_workspace_bytes': (c_int64, [c_int64, I, I, I]),
+        'leod_track_filter': (I, [VP, VP, VP, VP, VP, c_int64, I, I, POINTER(ctypes.c_double), I, ctypes.c_double, ctypes.c_double, F, I, I, I, F, I,
+                                  VP, VP, VP, VP, VP, VP, VP, VP, VP]),
+        'leod_pack_bbox': (I, [VP, c_int64, VP, I, VP]),
         'leod_voxel_bin': (I, [VP, VP, VP, VP, c_int64, I, I, I, I, I, VP, VP]),
         'leod_adamw_ema': (I, [VP, VP, VP, VP, VP, c_int64, I, F, F, F, F, F, F, F, VP]),
     }
@@ -117,7 +121,7 @@ EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 
                     'leod_detect_param_info', 'leod_detect_buffer_info', 'leod_detect_counter_info', 'leod_detect_param_count',
                     'leod_detect_buffer_count', 'leod_detect_counter_count', 'leod_detect_num_anchors', 'leod_detect_bind',
                     'leod_detect_prepare', 'leod_detect_reserve', 'leod_detect_set_allreduce', 'leod_fpn_head_fwd',
-                    'leod_simota_loss_fwd', 'leod_simota_loss_bwd', 'leod_simota_assignment', 'leod_detect_get_raw', 'leod_detect_get_raw_grad', 'leod_detect_set_raw_grad', 'leod_fpn_head_bwd', 'leod_postprocess', 'leod_pred2label', 'leod_tta_merge',
+                    'leod_simota_loss_fwd', 'leod_simota_loss_bwd', 'leod_simota_assignment', 'leod_detect_get_raw', 'leod_detect_get_raw_grad', 'leod_detect_set_raw_grad', 'leod_fpn_head_bwd', 'leod_postprocess', 'leod_pred2label', 'leod_tta_merge', 'leod_track_workspace_bytes', 'leod_track_filter', 'leod_pack_bbox',
                     'leod_voxel_bin', 'leod_adamw_ema']
 
 
