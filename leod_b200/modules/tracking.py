@@ -105,3 +105,91 @@ def summarize(frame_idx: Sequence[int], frames_rows: List[torch.Tensor]):
         n += r.shape[0]
     rows = torch.cat(list(frames_rows)) if frames_rows else torch.zeros(0, 8, device='cuda')
     return pack_labels(rows, packed=True), np.asarray(starts, np.int64), np.asarray(list(frame_idx), np.int64)
+
+
+class EventSeqData:
+    """Labels of one event sequence collected during the sweep — mirror of modules/pseudo_labeler.py:94-400 (`update` with the
+    hflip / tflip bookkeeping :107-155, `_aggregate_results` :157-177, `_track_filter` :268-333, `_summarize` :179-199, `save`
+    :335-397).  Rows stay on the device; the TTA merge, the tracker and the record packer are library calls.  `finalize_sequences`
+    post-processes many finished sequences with ONE tracker launch (the reference tracks them one by one in Python)."""
+
+    def __init__(self, path: str, scale_ratio: float, filter_config, postproc_cfg, hw):
+        self.path, self.scale_ratio, self.filter_config, self.postproc_cfg = path, scale_ratio, filter_config, postproc_cfg
+        self.hw = tuple(hw)
+        self._eoe, self._aug = False, False
+        self.frame_idx_2_labels = {}
+        self.frame_idx, self.labels = [], []
+
+    @property
+    def eoe(self) -> bool:
+        return self._eoe
+
+    def update(self, labels, ev_idx, is_last_sample: bool, is_padded_mask, is_hflip: bool, is_tflip: bool, tflip_offset: int = 0) -> None:
+        """pseudo_labeler.py:107-155.  labels: per-timestep ObjectLabels | None of one chunk; ev_idx: their frame indices (-1 = padding)."""
+        self._eoe = bool(is_last_sample)
+        if is_hflip:
+            for l in labels:
+                if l is not None:
+                    l.flip_lr_()
+            self._aug = True
+        if is_tflip:
+            ev_idx = [i + tflip_offset for i in ev_idx]
+            self._aug = True
+        for tidx, (label, f) in enumerate(zip(labels, ev_idx)):
+            if f < 0 or label is None or len(label) == 0:
+                continue
+            assert not is_padded_mask[tidx]
+            rows = label.object_labels
+            if self.scale_ratio != 1:                       # labels are stored at sensor resolution (ObjectLabels.scale_)
+                rows = rows.clone()
+                rows[:, 1:5] = rows[:, 1:5] * self.scale_ratio
+            if f in self.frame_idx_2_labels:
+                if bool((rows[:, 0] > 0).any()):            # ground truth is added once (:139-149)
+                    continue
+                self.frame_idx_2_labels[f] = torch.cat((self.frame_idx_2_labels[f], rows), 0)
+            else:
+                self.frame_idx_2_labels[f] = rows
+
+    def aggregate_results(self, num_frames: int) -> None:
+        """pseudo_labeler.py:157-177: sort by frame, merge the TTA views of every frame with a second NMS."""
+        from leod_b200.data.labels import ObjectLabels
+        from leod_b200.modules.pseudo_labeler import tta_postprocess
+        assert self._eoe, 'Cannot aggregate results before the sequence ends.'
+        self.frame_idx = sorted(i for i in self.frame_idx_2_labels if 0 <= i < num_frames)
+        self.labels = [self.frame_idx_2_labels[i] for i in self.frame_idx]
+        if self._aug and self.labels:
+            hw = tuple(int(v * self.scale_ratio) for v in self.hw)
+            merged = tta_postprocess([ObjectLabels(r, hw) for r in self.labels], conf_thre=self.postproc_cfg.confidence_threshold,
+                                     nms_thre=self.postproc_cfg.nms_threshold)
+            self.labels = [m.object_labels for m in merged]
+
+    def save(self, save_dir: str, num_frames: int, labels_fn: str = 'labels_v2/labels.npz', repr_dir: str = 'event_representations_v2'):
+        """The files of pseudo_labeler.py:335-381 for this sequence (the h5 soft link of :362 is the caller's: h5py is not a dependency):
+        <save_dir>/<seq>/labels_v2/labels.npz {labels, objframe_idx_2_label_idx}, <save_dir>/<seq>/<repr_dir>/objframe_idx_2_repr_idx.npy."""
+        import os
+        if not self.labels and self.frame_idx_2_labels:
+            finalize_sequences([self], [num_frames])
+        labels, lbl_idx, repr_idx = summarize(self.frame_idx, self.labels)
+        seq_dir = os.path.join(save_dir, os.path.basename(self.path))
+        os.makedirs(os.path.join(seq_dir, os.path.dirname(labels_fn)), exist_ok=True)
+        os.makedirs(os.path.join(seq_dir, repr_dir), exist_ok=True)
+        np.save(os.path.join(seq_dir, repr_dir, 'objframe_idx_2_repr_idx.npy'), repr_idx)
+        np.savez(os.path.join(seq_dir, labels_fn), labels=labels, objframe_idx_2_label_idx=lbl_idx)
+        return seq_dir
+
+
+def finalize_sequences(seqs: Sequence[EventSeqData], num_frames: Sequence[int]) -> None:
+    """`_aggregate_results` per sequence, then `_track_filter` for ALL of them in one tracker launch (pseudo_labeler.py:366-367)."""
+    for s, n in zip(seqs, num_frames):
+        s.aggregate_results(n)
+    if not seqs:
+        return
+    fc = seqs[0].filter_config
+    mtl = int(fc.get('min_track_len', 6))
+    if mtl <= 0:
+        return
+    res = track_filter_sequences([(s.frame_idx, s.labels) for s in seqs], [tuple(int(v * s.scale_ratio) for v in s.hw) for s in seqs],
+                                 min_track_len=mtl, track_method=fc.get('track_method', 'forward or backward'), inpaint=bool(fc.get('inpaint', True)),
+                                 ignore_label=int(fc.get('ignore_label', 1024)))
+    for s, (fi, rows) in zip(seqs, res):
+        s.frame_idx, s.labels = fi, rows

@@ -105,3 +105,56 @@ def test_many_sequences_one_call_vs_oracle():
             n_ignored += int((np.asarray(b)[:, 5] == 1024).sum())
         n_inpainted += sum(len(r) for r in ref_rows) - sum(len(r) for r in frames)
     assert n_ignored > 50 and n_inpainted > 20, (n_ignored, n_inpainted)
+
+
+def test_event_seq_data_update_aggregate_track_save(tmp_path):
+    """EventSeqData (modules/pseudo_labeler.py:94-400): chunks of a normal, an hflip and a tflip view collected per frame, merged by the
+    TTA NMS, tracked / filtered / in-painted, written as labels.npz — against the composition of the oracle's pieces."""
+    from oracle import postprocess as opp
+    from leod_b200.config import Node
+    from leod_b200.data.labels import ObjectLabels
+    from leod_b200.modules.tracking import EventSeqData, finalize_sequences
+    hw, n_frames, off = (240, 304), 30, 1
+    idx, frames = _synth(9, n_frames, hw, 5, 0.2, 0.4, 0)
+    fc = Node(min_track_len=6, track_method='forward or backward', inpaint=True, ignore_label=1024)
+    pc = Node(confidence_threshold=0.1, nms_threshold=0.45)
+    seq = EventSeqData('/data/gen1/train/seq_a', 1, fc, pc, hw)
+    per_frame = {}
+    rng = np.random.default_rng(0)
+    for view in ('plain', 'hflip', 'tflip'):
+        rows_v = {f: r + (rng.normal(0, 0.5, r.shape).astype(np.float32) * np.array([0, 1, 1, 1, 1, 0, 0, 0], np.float32)) for f, r in zip(idx, frames)}
+        for c0 in range(0, n_frames, 10):                   # three chunks of 10 timesteps
+            ts = list(range(c0, c0 + 10))
+            labels, ev_idx = [], []
+            for t in ts:
+                r = rows_v.get(t)
+                if view == 'tflip':
+                    ev_idx.append(t - off)                  # the time-flipped stream reports indices shifted by tflip_offset
+                else:
+                    ev_idx.append(t)
+                if r is None:
+                    labels.append(None)
+                    continue
+                lab = ObjectLabels(torch.from_numpy(r.copy()).cuda(), hw)
+                if view == 'hflip':
+                    lab.flip_lr_()                          # what the model saw; update() flips it back
+                labels.append(lab)
+                per_frame.setdefault(t, []).append(r)
+            seq.update(labels, ev_idx, is_last_sample=c0 + 10 >= n_frames, is_padded_mask=[False] * 10, is_hflip=view == 'hflip',
+                       is_tflip=view == 'tflip', tflip_offset=off)
+    finalize_sequences([seq], [n_frames])
+    # oracle composition
+    fi_ref = sorted(per_frame)
+    merged = [opp.tta_merge(np.concatenate(per_frame[f]), 0.1, 0.45) for f in fi_ref]
+    fi_ref, rows_ref = otr.track_filter(merged, fi_ref, hw, 6, 'forward or backward', True, 1024)
+    assert seq.frame_idx == fi_ref
+    for a, b in zip(seq.labels, rows_ref):
+        got, ref = a.cpu().numpy(), np.asarray(b, np.float32)
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5)     # the hflip round trip (W-1-x-w twice) costs an ulp
+    d = seq.save(str(tmp_path), n_frames)
+    z = np.load(os.path.join(d, 'labels_v2', 'labels.npz'))
+    rec, lbl_idx, _ = labels_io.summarize(seq.frame_idx, [r.cpu().numpy() for r in seq.labels])
+    assert z['labels'].tobytes() == rec.tobytes() and z['labels'].dtype.names == rec.dtype.names
+    np.testing.assert_array_equal(z['objframe_idx_2_label_idx'], lbl_idx)
+    np.testing.assert_array_equal(np.load(os.path.join(d, 'event_representations_v2', 'objframe_idx_2_repr_idx.npy')), np.asarray(seq.frame_idx))
