@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting and the thin exported wrappers around the building-block kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,10 @@ void leod_set_error(const char *fmt, ...) {
 }
 
 unsigned long long g_leod_launches = 0;
+int g_leod_pdl = [] {
+  const char *e = getenv("LEOD_PDL");     // 0: plain stream-ordered launches
+  return e ? atoi(e) : 1;
+}();
 
 // ------------------------------------------------------------------ event profiler
 #include <vector>

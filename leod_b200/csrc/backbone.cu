@@ -148,6 +148,7 @@ GemmNT mk(const void *A, int lda, const void *B, int ldb, void *C, int ldc, int 
 }
 
 __global__ void conv_grad_unpermute_kernel(float *__restrict__ G, float *__restrict__ dW, int N, int Cin, int ksz) {
+  pdl_prologue();
   const int K = Cin * ksz * ksz;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * K) return;
@@ -158,6 +159,7 @@ __global__ void conv_grad_unpermute_kernel(float *__restrict__ G, float *__restr
 }
 // stem layout: k = (cin*ksz + ky)*8 + slot, slots 1..ksz <-> kx (kernels_elem.cu, im2col_nchw_kernel)
 __global__ void stem_grad_unpermute_kernel(float *__restrict__ G, float *__restrict__ dW, int N, int Cin, int ksz) {
+  pdl_prologue();
   const int K = Cin * ksz * 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * K) return;
@@ -895,9 +897,9 @@ extern "C" int leod_backbone_grads_finalize(leod_backbone_t *h, void *stream) {
     {
       const int64_t n = (int64_t)C * d.K;
       if (s > 0)
-        conv_grad_unpermute_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w.Gconv, G + p.convw, C, d.Cin, d.ksz);
+        LEOD_LAUNCH((conv_grad_unpermute_kernel), (int)((n + 255) / 256), 256, 0, st, w.Gconv, G + p.convw, C, d.Cin, d.ksz);
       else
-        stem_grad_unpermute_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(w.Gconv, G + p.convw, C, d.Cin, d.ksz);
+        LEOD_LAUNCH((stem_grad_unpermute_kernel), (int)((n + 255) / 256), 256, 0, st, w.Gconv, G + p.convw, C, d.Cin, d.ksz);
       LEOD_LAUNCH_CHECK();
     }
     for (int b = 0; b < 2; ++b) {

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <utility>
+
 #include "../../include/leod_b200.h"
 
 typedef __nv_bfloat16 bf16;
@@ -34,6 +36,36 @@ extern unsigned long long g_leod_launches;  // kernels launched by this library 
     ++g_leod_launches;             \
     LEOD_CUDA(cudaGetLastError()); \
   } while (0)
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of this library is launched with cudaLaunchAttributeProgrammaticStreamSerialization (LEOD_PDL=0 disables): its CTAs
+// may be scheduled while the previous kernel of the stream is still draining (the tail of a persistent GEMM, the last wave of an
+// elementwise kernel), run their prologue (barrier init, TMEM allocation, tensor-map fetch) and then block in pdl_wait() until the
+// predecessor has completed and its memory is visible.  Every kernel calls pdl_prologue() / pdl_wait() before its first access
+// to global memory, reads AND writes, so the overlap never changes results.  The steps of this path are chains of several hundred
+// short dependent kernels: the launch gap between them is the cost this removes.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+extern int g_leod_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t leod_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_leod_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#define LEOD_LAUNCH(kernel, grid, block, smem, st, ...) (void)leod_launch(kernel, dim3(grid), dim3(block), (size_t)(smem), st, ##__VA_ARGS__)
 
 // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py roofline pass).
 enum ProfKind { PK_GEMM_NT = 0, PK_GEMM_TN, PK_ATTN_FWD, PK_ATTN_BWD, PK_LAYERNORM, PK_LSTM, PK_PATCH, PK_OTHER, PK_CONV, PK_COUNT };

@@ -289,6 +289,7 @@ int dev_alloc(leod_detect *h, void **p, size_t bytes) {
 //   tmode 1: dstT[tap*cinp + ci', row0 + n]    (B operand [taps*cinp, coutp] of the stride-2 input gradient through the patch matrix)
 template <typename T>
 __global__ void prep_batched_kernel(const PrepDesc *__restrict__ descs, const float *__restrict__ params) {
+  pdl_prologue();
   const PrepDesc d = descs[blockIdx.y];
   const int taps = d.k * d.k;
   const int64_t total = (int64_t)d.Cout * taps * d.Cin;
@@ -309,6 +310,7 @@ __global__ void prep_batched_kernel(const PrepDesc *__restrict__ descs, const fl
 }
 // G fp32 (prepared layout) -> dW [Cout, Cin, k, k] += ; G cleared
 __global__ void unprep_batched_kernel(const PrepDesc *__restrict__ descs, float *__restrict__ grads) {
+  pdl_prologue();
   const PrepDesc d = descs[blockIdx.y];
   if (!d.G) return;
   const int taps = d.k * d.k;
@@ -335,6 +337,7 @@ struct PredPrep3 { PredPrep p[3]; };
 // 0..3 = reg_preds (reg tower), 4 = obj_preds (reg tower), 5.. = cls_preds (cls tower)  (yolo_head.py:214-222, :236)
 template <typename T>
 __global__ void prep_pred_kernel(PredPrep3 pp, const float *__restrict__ params, int hid, int C) {
+  pdl_prologue();
   const PredPrep p = pp.p[blockIdx.x];
   T *B = (T *)p.B, *BT = (T *)p.BT;
   for (int i = threadIdx.x; i < (5 + C) * hid; i += blockDim.x) {
@@ -353,6 +356,7 @@ __global__ void prep_pred_kernel(PredPrep3 pp, const float *__restrict__ params,
   }
 }
 __global__ void unprep_pred_kernel(PredPrep3 pp, float *__restrict__ grads, int hid, int C) {
+  pdl_prologue();
   const PredPrep p = pp.p[blockIdx.x];
   for (int i = threadIdx.x; i < (5 + C) * hid; i += blockDim.x) {
     const int row = i / hid, k = i % hid;
@@ -791,13 +795,13 @@ extern "C" int leod_detect_prepare(leod_detect_t *h, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid(std::max(1, std::min(64, ceil_div(h->max_prep_items, 256))), h->n_prep);
   if (h->cfg.dtype == LEOD_F32) {
-    prep_batched_kernel<float><<<grid, 256, 0, st>>>(h->prep_dev, h->params);
+    LEOD_LAUNCH((prep_batched_kernel<float>), grid, 256, 0, st, h->prep_dev, h->params);
     LEOD_LAUNCH_CHECK();
-    prep_pred_kernel<float><<<3, 256, 0, st>>>(pred_prep_args(h), h->params, h->hid, h->cfg.num_classes);
+    LEOD_LAUNCH((prep_pred_kernel<float>), 3, 256, 0, st, pred_prep_args(h), h->params, h->hid, h->cfg.num_classes);
   } else {
-    prep_batched_kernel<bf16><<<grid, 256, 0, st>>>(h->prep_dev, h->params);
+    LEOD_LAUNCH((prep_batched_kernel<bf16>), grid, 256, 0, st, h->prep_dev, h->params);
     LEOD_LAUNCH_CHECK();
-    prep_pred_kernel<bf16><<<3, 256, 0, st>>>(pred_prep_args(h), h->params, h->hid, h->cfg.num_classes);
+    LEOD_LAUNCH((prep_pred_kernel<bf16>), 3, 256, 0, st, pred_prep_args(h), h->params, h->hid, h->cfg.num_classes);
   }
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -983,9 +987,9 @@ extern "C" int leod_fpn_head_bwd(leod_detect_t *h, void *const dfeats[3], void *
   }
   {
     dim3 grid(std::max(1, std::min(64, ceil_div(h->max_prep_items, 256))), h->n_prep);
-    unprep_batched_kernel<<<grid, 256, 0, st>>>(h->prep_dev, h->grads);
+    LEOD_LAUNCH((unprep_batched_kernel), grid, 256, 0, st, h->prep_dev, h->grads);
     LEOD_LAUNCH_CHECK();
-    unprep_pred_kernel<<<3, 256, 0, st>>>(pred_prep_args(h), h->grads, h->hid, h->cfg.num_classes);
+    LEOD_LAUNCH((unprep_pred_kernel), 3, 256, 0, st, pred_prep_args(h), h->grads, h->hid, h->cfg.num_classes);
     LEOD_LAUNCH_CHECK();
   }
   if (dfeats)

@@ -23,6 +23,7 @@ constexpr int ATT_THREADS = 128;
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(const T *__restrict__ qkv, T *__restrict__ out, int H, int W, int C,
                                                                int dh, int ph, int pw, int window, float scale) {
+  pdl_prologue();
   extern __shared__ float sm[];
   const int Tn = ph * pw, ldh = dh + 1, lds = Tn + 1;
   float *q = sm, *k = q + Tn * ldh, *v = k + Tn * ldh, *S = v + Tn * ldh;
@@ -72,6 +73,7 @@ template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(const T *__restrict__ qkv, const T *__restrict__ dout,
                                                                T *__restrict__ dqkv, int H, int W, int C, int dh, int ph, int pw,
                                                                int window, float scale) {
+  pdl_prologue();
   extern __shared__ float sm[];
   const int Tn = ph * pw, ldh = dh + 1, lds = Tn + 1;
   float *q = sm, *k = q + Tn * ldh, *v = k + Tn * ldh, *dO = v + Tn * ldh;
@@ -157,10 +159,10 @@ int attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, in
   ProfScope ps(PK_ATTN_FWD, 4.0 * groups * heads * Tn * Tn * dh, 4.0 * B * H * W * C * dtype_size(dtype), st);
   if (dtype == LEOD_F32) {
     LEOD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_kernel<float><<<grid, ATT_THREADS, smem, st>>>((const float *)qkv, (float *)out, H, W, C, dh, ph, pw, window, scale);
+    LEOD_LAUNCH((attn_fwd_kernel<float>), grid, ATT_THREADS, smem, st, (const float *)qkv, (float *)out, H, W, C, dh, ph, pw, window, scale);
   } else {
     LEOD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_kernel<bf16><<<grid, ATT_THREADS, smem, st>>>((const bf16 *)qkv, (bf16 *)out, H, W, C, dh, ph, pw, window, scale);
+    LEOD_LAUNCH((attn_fwd_kernel<bf16>), grid, ATT_THREADS, smem, st, (const bf16 *)qkv, (bf16 *)out, H, W, C, dh, ph, pw, window, scale);
   }
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -182,11 +184,11 @@ int attention_bwd(int dtype, const void *qkv, const void *dout, void *dqkv, int 
   ProfScope ps(PK_ATTN_BWD, 10.0 * groups * heads * Tn * Tn * dh, 7.0 * B * H * W * C * dtype_size(dtype), st);
   if (dtype == LEOD_F32) {
     LEOD_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_kernel<float><<<grid, ATT_THREADS, smem, st>>>((const float *)qkv, (const float *)dout, (float *)dqkv, H, W, C, dh,
+    LEOD_LAUNCH((attn_bwd_kernel<float>), grid, ATT_THREADS, smem, st, (const float *)qkv, (const float *)dout, (float *)dqkv, H, W, C, dh,
                                                            ph, pw, window, scale);
   } else {
     LEOD_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_bwd_kernel<bf16><<<grid, ATT_THREADS, smem, st>>>((const bf16 *)qkv, (const bf16 *)dout, (bf16 *)dqkv, H, W, C, dh, ph, pw,
+    LEOD_LAUNCH((attn_bwd_kernel<bf16>), grid, ATT_THREADS, smem, st, (const bf16 *)qkv, (const bf16 *)dout, (bf16 *)dqkv, H, W, C, dh, ph, pw,
                                                           window, scale);
   }
   LEOD_LAUNCH_CHECK();

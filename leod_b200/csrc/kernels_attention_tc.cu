@@ -129,6 +129,7 @@ template <int NT_S, int NT_O, int KS>
 __global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16))
     attn_fwd_tc_kernel(const bf16 *__restrict__ qkv, bf16 *__restrict__ out, int H, int W, int C, int ph, int pw, int window,
                        float scale) {
+  pdl_prologue();
   constexpr int TP = ((NT_S * 8 + 15) / 16) * 16;  // padded tokens
   constexpr int DH = NT_O * 8, DHP = KS * 16;
   constexpr int LDQ = DHP + 8;
@@ -203,6 +204,7 @@ template <int NT_S, int NT_O, int KS>
 __global__ void __launch_bounds__(32 * ((NT_S * 8 + 15) / 16), 4)
     attn_bwd_tc_kernel(const bf16 *__restrict__ qkv, const bf16 *__restrict__ dout, bf16 *__restrict__ dqkv, int H, int W, int C,
                        int ph, int pw, int window, float scale) {
+  pdl_prologue();
   constexpr int TP = ((NT_S * 8 + 15) / 16) * 16;
   constexpr int DH = NT_O * 8, DHP = KS * 16;
   constexpr int LDQ = DHP + 8, LDT = TP + 8, LDO = 3 * DH + 8;
@@ -354,7 +356,7 @@ template <int NT_S, int NT_O, int KS>
 int launch_fwd(const bf16 *qkv, bf16 *out, int groups, int heads, int H, int W, int C, int ph, int pw, int window, float scale,
                cudaStream_t st) {
   constexpr int TP = ((NT_S * 8 + 15) / 16) * 16;
-  attn_fwd_tc_kernel<NT_S, NT_O, KS><<<dim3(groups, heads), 32 * (TP / 16), 0, st>>>(qkv, out, H, W, C, ph, pw, window, scale);
+  LEOD_LAUNCH((attn_fwd_tc_kernel<NT_S, NT_O, KS>), dim3(groups, heads), 32 * (TP / 16), 0, st, qkv, out, H, W, C, ph, pw, window, scale);
   return 0;
 }
 template <int NT_S, int NT_O, int KS>
@@ -368,7 +370,7 @@ int launch_bwd(const bf16 *qkv, const bf16 *dout, bf16 *dqkv, int groups, int he
     LEOD_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<NT_S, NT_O, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set = true;
   }
-  attn_bwd_tc_kernel<NT_S, NT_O, KS><<<dim3(groups, heads), 32 * (TP / 16), smem, st>>>(qkv, dout, dqkv, H, W, C, ph, pw, window, scale);
+  LEOD_LAUNCH((attn_bwd_tc_kernel<NT_S, NT_O, KS>), dim3(groups, heads), 32 * (TP / 16), smem, st, qkv, dout, dqkv, H, W, C, ph, pw, window, scale);
   return 0;
 }
 

@@ -67,6 +67,7 @@ __device__ __forceinline__ bool pad_pixel(int q, const PadGeom &g, int &y, int &
 // ------------------------------------------------------------------ layout changes
 template <typename T>
 __global__ void pad_gather_kernel(const T *__restrict__ src, T *__restrict__ dst, int ldd, PadGeom g, int C) {
+  pdl_prologue();
   const int nc = C >> 3;
   const int64_t total = g.R * nc;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -82,6 +83,7 @@ __global__ void pad_gather_kernel(const T *__restrict__ src, T *__restrict__ dst
 // interior rows of a padded matrix -> dense NHWC
 template <typename T>
 __global__ void pad_scatter_kernel(const T *__restrict__ src, int lds, T *__restrict__ dst, PadGeom g, int C) {
+  pdl_prologue();
   const int nc = C >> 3;
   const int64_t total = (int64_t)g.B * g.h * g.w * nc;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -95,6 +97,7 @@ __global__ void pad_scatter_kernel(const T *__restrict__ src, int lds, T *__rest
 // nearest-exact x2 (F.interpolate(scale_factor=2, mode='nearest-exact'), yolo_pafpn.py:49): dst(y, x) = src(y/2, x/2)
 template <typename T>
 __global__ void upsample2x_kernel(const T *__restrict__ src, int lds, PadGeom gs, T *__restrict__ dst, int ldd, PadGeom gd, int C) {
+  pdl_prologue();
   const int nc = C >> 3;
   const int64_t total = gd.R * nc;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -110,6 +113,7 @@ __global__ void upsample2x_kernel(const T *__restrict__ src, int lds, PadGeom gs
 template <typename T>
 __global__ void upsample2x_bwd_kernel(const T *__restrict__ ddst, int ldd, PadGeom gd, T *__restrict__ dsrc, int lds, PadGeom gs, int C,
                                       int accumulate) {
+  pdl_prologue();
   const int nc = C >> 3;
   const int64_t total = gs.R * nc;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -135,6 +139,7 @@ __global__ void upsample2x_bwd_kernel(const T *__restrict__ ddst, int ldd, PadGe
 template <typename T>
 __global__ void im2col_pad_s2_kernel(const T *__restrict__ src, int lds, PadGeom gs, T *__restrict__ col, int ldcol, PadGeom go, int cin,
                                      int cinp) {
+  pdl_prologue();
   const int nc = cinp >> 3;
   const int64_t total = go.R * 9 * nc;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -154,6 +159,7 @@ __global__ void im2col_pad_s2_kernel(const T *__restrict__ src, int lds, PadGeom
 template <typename T>
 __global__ void col2im_pad_s2_kernel(const T *__restrict__ dcol, int ldcol, PadGeom go, T *__restrict__ dsrc, int lds, PadGeom gs, int cin,
                                      int cinp, int accumulate) {
+  pdl_prologue();
   const int nc = cin >> 3;
   const int64_t total = gs.R * nc;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -232,6 +238,7 @@ __device__ __forceinline__ bool last_block(double *ticket_slot) {
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *__restrict__ Y, int ldy, PadGeom g, int C, BnFin f, int finalize,
                                                               int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[BN_THREADS][17];
   double *stats = f.stats;
   const int nc = C >> 3;
@@ -278,7 +285,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T *__restric
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&stats[2 * C], (double)g.B * g.h * g.w);
   if (finalize && last_block(&stats[2 * C + 1])) bn_finalize_channels(f, C, tid, blockDim.x);
 }
-__global__ void __launch_bounds__(BN_THREADS) bn_finalize_kernel(BnFin f, int C) { bn_finalize_channels(f, C, threadIdx.x, blockDim.x); }
+__global__ void __launch_bounds__(BN_THREADS) bn_finalize_kernel(BnFin f, int C) {
+  pdl_prologue(); bn_finalize_channels(f, C, threadIdx.x, blockDim.x); }
 
 // 8 consecutive floats as two 16-byte loads
 __device__ __forceinline__ V8 ldg8(const float *p) {
@@ -294,6 +302,7 @@ __device__ __forceinline__ V8 ldg8(const float *p) {
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) bn_apply_silu_kernel(const T *__restrict__ Y, int ldy, PadGeom g, int C, const float *__restrict__ fin,
                                                                    BnSeg s0, BnSeg s1, int cseg, T *__restrict__ Z, int ldz, float eps, int training) {
+  pdl_prologue();
   const int nc = C >> 3;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.R * nc) return;
@@ -352,6 +361,7 @@ __device__ __forceinline__ void bn_bwd_finalize_channels(const BnBwdFin &f, int 
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T *__restrict__ dZ, int lddz, const T *__restrict__ Y, int ldy, PadGeom g, int C,
                                                                    const float *__restrict__ fin, BnBwdFin f, int finalize, int rows_per_block) {
+  pdl_prologue();
   __shared__ float red[BN_THREADS][17];
   const int nc = C >> 3;
   const int tid = threadIdx.x;
@@ -409,13 +419,15 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T *__re
   }
   if (finalize && last_block(&f.dloc[2 * C])) bn_bwd_finalize_channels(f, C, tid, blockDim.x);
 }
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_finalize_kernel(BnBwdFin f, int C) { bn_bwd_finalize_channels(f, C, threadIdx.x, blockDim.x); }
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_finalize_kernel(BnBwdFin f, int C) {
+  pdl_prologue(); bn_bwd_finalize_channels(f, C, threadIdx.x, blockDim.x); }
 
 // dy = gamma * rstd * (dyhat - mean(dyhat) - xhat * mean(dyhat * xhat)), 0 on the border
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T *__restrict__ dZ, int lddz, const T *__restrict__ Y, int ldy, PadGeom g, int C,
                                                                   const float *__restrict__ fin, const float *__restrict__ dfin, BnSeg s0, BnSeg s1,
                                                                   int cseg, T *__restrict__ dY, int lddy) {
+  pdl_prologue();
   const int nc = C >> 3;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.R * nc) return;
@@ -443,6 +455,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T *__res
 }
 
 template <typename T> __global__ void fill_zero_kernel(T *p, int64_t n) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = T(0);
 }
 
@@ -486,40 +499,40 @@ PadGeom make_pad_geom(int B, int h, int w) {
 
 int pad_gather(int dtype, const void *src, void *dst, int ldd, const PadGeom &g, int C, cudaStream_t st) {
   LEOD_REQUIRE(C % 8 == 0 && ldd % 8 == 0, "pad_gather: C %d / ld %d must be multiples of 8", C, ldd);
-  DISPATCH_T(dtype, (pad_gather_kernel<T><<<grid_for(g.R * (C / 8)), 256, 0, st>>>((const T *)src, (T *)dst, ldd, g, C)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((pad_gather_kernel<T>), grid_for(g.R * (C / 8)), 256, 0, st, (const T *)src, (T *)dst, ldd, g, C)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 int pad_scatter(int dtype, const void *src, int lds, void *dst, const PadGeom &g, int C, cudaStream_t st) {
   LEOD_REQUIRE(C % 8 == 0 && lds % 8 == 0, "pad_scatter: C %d / ld %d must be multiples of 8", C, lds);
-  DISPATCH_T(dtype, (pad_scatter_kernel<T><<<grid_for((int64_t)g.B * g.h * g.w * (C / 8)), 256, 0, st>>>((const T *)src, lds, (T *)dst, g, C)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((pad_scatter_kernel<T>), grid_for((int64_t)g.B * g.h * g.w * (C / 8)), 256, 0, st, (const T *)src, lds, (T *)dst, g, C)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 int upsample2x(int dtype, const void *src, int lds, const PadGeom &gs, void *dst, int ldd, const PadGeom &gd, int C, cudaStream_t st) {
   LEOD_REQUIRE(gd.h == 2 * gs.h && gd.w == 2 * gs.w && gd.B == gs.B && C % 8 == 0, "upsample2x: shape mismatch");
-  DISPATCH_T(dtype, (upsample2x_kernel<T><<<grid_for(gd.R * (C / 8)), 256, 0, st>>>((const T *)src, lds, gs, (T *)dst, ldd, gd, C)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((upsample2x_kernel<T>), grid_for(gd.R * (C / 8)), 256, 0, st, (const T *)src, lds, gs, (T *)dst, ldd, gd, C)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 int upsample2x_bwd(int dtype, const void *ddst, int ldd, const PadGeom &gd, void *dsrc, int lds, const PadGeom &gs, int C, int accumulate,
                    cudaStream_t st) {
   LEOD_REQUIRE(gd.h == 2 * gs.h && gd.w == 2 * gs.w && gd.B == gs.B && C % 8 == 0, "upsample2x_bwd: shape mismatch");
-  DISPATCH_T(dtype, (upsample2x_bwd_kernel<T><<<grid_for(gs.R * (C / 8)), 256, 0, st>>>((const T *)ddst, ldd, gd, (T *)dsrc, lds, gs, C, accumulate)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((upsample2x_bwd_kernel<T>), grid_for(gs.R * (C / 8)), 256, 0, st, (const T *)ddst, ldd, gd, (T *)dsrc, lds, gs, C, accumulate)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 int im2col_pad_s2(int dtype, const void *src, int lds, const PadGeom &gs, void *col, int ldcol, const PadGeom &go, int cin, int cinp,
                   cudaStream_t st) {
   LEOD_REQUIRE(gs.h == 2 * go.h && gs.w == 2 * go.w && cin % 8 == 0 && cinp % 8 == 0, "im2col_pad_s2: shape mismatch");
-  DISPATCH_T(dtype, (im2col_pad_s2_kernel<T><<<grid_for(go.R * 9 * (cinp / 8)), 256, 0, st>>>((const T *)src, lds, gs, (T *)col, ldcol, go, cin, cinp)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((im2col_pad_s2_kernel<T>), grid_for(go.R * 9 * (cinp / 8)), 256, 0, st, (const T *)src, lds, gs, (T *)col, ldcol, go, cin, cinp)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 int col2im_pad_s2(int dtype, const void *dcol, int ldcol, const PadGeom &go, void *dsrc, int lds, const PadGeom &gs, int cin, int cinp,
                   int accumulate, cudaStream_t st) {
   LEOD_REQUIRE(gs.h == 2 * go.h && gs.w == 2 * go.w && cin % 8 == 0, "col2im_pad_s2: shape mismatch");
-  DISPATCH_T(dtype, (col2im_pad_s2_kernel<T><<<grid_for(gs.R * (cin / 8)), 256, 0, st>>>((const T *)dcol, ldcol, go, (T *)dsrc, lds, gs, cin, cinp, accumulate)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((col2im_pad_s2_kernel<T>), grid_for(gs.R * (cin / 8)), 256, 0, st, (const T *)dcol, ldcol, go, (T *)dsrc, lds, gs, cin, cinp, accumulate)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -530,19 +543,19 @@ int bn_stats(int dtype, const void *Y, int ldy, const PadGeom &g, const BnLayer 
   int threads, rpb, blocks;
   bn_launch_shape(l.C, g.R, &threads, &rpb, &blocks);
   BnFin f{l.stats, l.fin, l.s0, l.s1, l.cseg, l.eps, l.momentum, 1};
-  DISPATCH_T(dtype, (bn_stats_kernel<T><<<blocks, threads, 0, st>>>((const T *)Y, ldy, g, l.C, f, finalize, rpb)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((bn_stats_kernel<T>), blocks, threads, 0, st, (const T *)Y, ldy, g, l.C, f, finalize, rpb)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 int bn_finalize(const BnLayer &l, cudaStream_t st) {
   BnFin f{l.stats, l.fin, l.s0, l.s1, l.cseg, l.eps, l.momentum, 1};
-  bn_finalize_kernel<<<1, BN_THREADS, 0, st>>>(f, l.C);
+  LEOD_LAUNCH((bn_finalize_kernel), 1, BN_THREADS, 0, st, f, l.C);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 int bn_apply_silu(int dtype, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, void *Z, int ldz, int training, cudaStream_t st) {
   const int blocks = ceil_div(g.R * (l.C / 8), BN_THREADS);
-  DISPATCH_T(dtype, (bn_apply_silu_kernel<T><<<blocks, BN_THREADS, 0, st>>>((const T *)Y, ldy, g, l.C, l.fin, l.s0, l.s1, l.cseg, (T *)Z, ldz, l.eps,
+  DISPATCH_T(dtype, (LEOD_LAUNCH((bn_apply_silu_kernel<T>), blocks, BN_THREADS, 0, st, (const T *)Y, ldy, g, l.C, l.fin, l.s0, l.s1, l.cseg, (T *)Z, ldz, l.eps,
                                                                             training)));
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -551,19 +564,19 @@ int bn_bwd_reduce(int dtype, const void *dZ, int lddz, const void *Y, int ldy, c
   int threads, rpb, blocks;
   bn_launch_shape(l.C, g.R, &threads, &rpb, &blocks);
   BnBwdFin f{l.dloc, l.dglob, l.stats, l.dfin, l.s0, l.s1, l.cseg};
-  DISPATCH_T(dtype, (bn_bwd_reduce_kernel<T><<<blocks, threads, 0, st>>>((const T *)dZ, lddz, (const T *)Y, ldy, g, l.C, l.fin, f, finalize, rpb)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((bn_bwd_reduce_kernel<T>), blocks, threads, 0, st, (const T *)dZ, lddz, (const T *)Y, ldy, g, l.C, l.fin, f, finalize, rpb)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 int bn_bwd_finalize(const BnLayer &l, cudaStream_t st) {
   BnBwdFin f{l.dloc, l.dglob, l.stats, l.dfin, l.s0, l.s1, l.cseg};
-  bn_bwd_finalize_kernel<<<1, BN_THREADS, 0, st>>>(f, l.C);
+  LEOD_LAUNCH((bn_bwd_finalize_kernel), 1, BN_THREADS, 0, st, f, l.C);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 int bn_bwd_apply(int dtype, const void *dZ, int lddz, const void *Y, int ldy, const PadGeom &g, const BnLayer &l, void *dY, int lddy, cudaStream_t st) {
   const int blocks = ceil_div(g.R * (l.C / 8), BN_THREADS);
-  DISPATCH_T(dtype, (bn_bwd_apply_kernel<T><<<blocks, BN_THREADS, 0, st>>>((const T *)dZ, lddz, (const T *)Y, ldy, g, l.C, l.fin, l.dfin, l.s0, l.s1,
+  DISPATCH_T(dtype, (LEOD_LAUNCH((bn_bwd_apply_kernel<T>), blocks, BN_THREADS, 0, st, (const T *)dZ, lddz, (const T *)Y, ldy, g, l.C, l.fin, l.dfin, l.s0, l.s1,
                                                                            l.cseg, (T *)dY, lddy)));
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -572,7 +585,7 @@ int bn_bwd_apply(int dtype, const void *dZ, int lddz, const void *Y, int ldy, co
 int device_zero_bytes(void *p, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return 0;
   LEOD_REQUIRE(bytes % 4 == 0, "device_zero_bytes: %zu not a multiple of 4", bytes);
-  fill_zero_kernel<uint32_t><<<grid_for((int64_t)(bytes / 4)), 256, 0, st>>>((uint32_t *)p, (int64_t)(bytes / 4));
+  LEOD_LAUNCH((fill_zero_kernel<uint32_t>), grid_for((int64_t)(bytes / 4)), 256, 0, st, (uint32_t *)p, (int64_t)(bytes / 4));
   LEOD_LAUNCH_CHECK();
   return 0;
 }

@@ -12,6 +12,7 @@ constexpr int PP_THREADS = 512;
 __global__ void __launch_bounds__(PP_THREADS) postprocess_kernel(const float *__restrict__ pred, int A, int ncls, float conf_thre,
                                                                  float nms_thre, int class_agnostic, float *__restrict__ out,
                                                                  int32_t *__restrict__ count, int max_det) {
+  pdl_prologue();
   extern __shared__ float sm[];
   // per candidate: score, anchor (unsorted) | sorted: anchor, offset box[4], suppressed flag
   float *c_score = sm;                          // [A]
@@ -124,6 +125,7 @@ struct P2LArgs {
 // one warp per image; order-preserving compaction with ballots
 __global__ void pred2label_kernel(const float *__restrict__ dets, const int32_t *__restrict__ count, int max_det, int ncls,
                                   P2LArgs th, int frame_h, int frame_w, float *__restrict__ labels, int32_t *__restrict__ lab_count) {
+  pdl_prologue();
   const int b = blockIdx.x, lane = threadIdx.x;
   const int n = count[b];
   const float *d = dets + (size_t)b * max_det * 7;
@@ -165,6 +167,7 @@ constexpr int TM_THREADS = 128;
 __global__ void __launch_bounds__(TM_THREADS) tta_merge_kernel(const float *__restrict__ labels, const int32_t *__restrict__ count,
                                                                int nmax, float conf_thre, float nms_thre, int class_agnostic,
                                                                float *__restrict__ out, int32_t *__restrict__ out_count) {
+  pdl_prologue();
   extern __shared__ float sm[];
   float *c_score = sm;                      // [nmax]
   int *c_row = (int *)(c_score + nmax);     // [nmax]
@@ -275,7 +278,7 @@ extern "C" int leod_postprocess(const float *pred, int B, int A, int num_classes
     LEOD_CUDA(cudaFuncSetAttribute(postprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  postprocess_kernel<<<B, PP_THREADS, smem, (cudaStream_t)stream>>>(pred, A, num_classes, conf_thre, nms_thre, class_agnostic, out,
+  LEOD_LAUNCH((postprocess_kernel), B, PP_THREADS, smem, (cudaStream_t)stream, pred, A, num_classes, conf_thre, nms_thre, class_agnostic, out,
                                                                     count, max_det);
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -292,7 +295,7 @@ extern "C" int leod_pred2label(const float *dets, const int32_t *count, int B, i
     th.obj_thr[i] = i < num_classes ? obj_thresh[i] : 2.f;
     th.cls_thr[i] = i < num_classes ? cls_thresh[i] : 2.f;
   }
-  pred2label_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(dets, count, max_det, num_classes, th, frame_h, frame_w, labels, lab_count);
+  LEOD_LAUNCH((pred2label_kernel), B, 32, 0, (cudaStream_t)stream, dets, count, max_det, num_classes, th, frame_h, frame_w, labels, lab_count);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -309,7 +312,7 @@ extern "C" int leod_tta_merge(const float *labels, const int32_t *count, int F, 
     LEOD_CUDA(cudaFuncSetAttribute(tta_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
   }
-  tta_merge_kernel<<<F, TM_THREADS, smem, (cudaStream_t)stream>>>(labels, count, nmax, conf_thre, nms_thre, class_agnostic, out,
+  LEOD_LAUNCH((tta_merge_kernel), F, TM_THREADS, smem, (cudaStream_t)stream, labels, count, nmax, conf_thre, nms_thre, class_agnostic, out,
                                                                   out_count);
   LEOD_LAUNCH_CHECK();
   return 0;

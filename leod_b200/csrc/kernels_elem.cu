@@ -13,6 +13,7 @@ constexpr int LN_MAX_C = 512;
 template <typename T, int LN_MAXV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
                                                      const float *__restrict__ b, T *__restrict__ y, int M, int C, float eps) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -46,6 +47,7 @@ template <typename T, int LN_MAXV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const T *__restrict__ x, const float *__restrict__ w,
                                                      const T *__restrict__ dy, const T *__restrict__ dres, T *__restrict__ dx,
                                                      float *__restrict__ dw, float *__restrict__ db, int M, int C, float eps) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   float dwacc[LN_MAXV], dbacc[LN_MAXV];
@@ -148,6 +150,7 @@ __device__ __forceinline__ float group_sum(float v) {
 template <int LPR, int NCH>
 __global__ void __launch_bounds__(256) ln_fwd_bf16_kernel(const bf16 *__restrict__ x, const float *__restrict__ w,
                                                           const float *__restrict__ b, bf16 *__restrict__ y, int M, int C, float eps) {
+  pdl_prologue();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR;
   const int row = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const bf16 *__restrict
                                                           const bf16 *__restrict__ dy, const bf16 *__restrict__ dres,
                                                           bf16 *__restrict__ dx, float *__restrict__ dw, float *__restrict__ db, int M,
                                                           int C, float eps) {
+  pdl_prologue();
   constexpr int RPW = 32 / LPR;
   __shared__ float sdw[LN_MAX_C], sdb[LN_MAX_C];
   for (int i = threadIdx.x; i < C; i += blockDim.x) sdw[i] = sdb[i] = 0.f;
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(256) ln_bwd_bf16_kernel(const bf16 *__restrict
 template <typename T>
 __global__ void lstm_fwd_kernel(T *__restrict__ gates, const T *__restrict__ c_prev, T *__restrict__ h_out,
                                 T *__restrict__ c_out, int M, int C) {
+  pdl_prologue();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)M * C) return;
   const int m = (int)(idx / C), c = (int)(idx % C);
@@ -330,6 +335,7 @@ template <typename T>
 __global__ void lstm_bwd_kernel(const T *__restrict__ gates, const T *__restrict__ c_prev, const T *__restrict__ c_out,
                                 const T *__restrict__ dh, const T *__restrict__ dh2, const T *__restrict__ dh3,
                                 const T *dc, T *__restrict__ dgates, T *dc_prev, int M, int C) {
+  pdl_prologue();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)M * C) return;
   const int m = (int)(idx / C), c = (int)(idx % C);
@@ -352,6 +358,7 @@ __global__ void lstm_bwd_kernel(const T *__restrict__ gates, const T *__restrict
 
 template <typename T>
 __global__ void add_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out, int64_t n) {
+  pdl_prologue();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < n) out[idx] = from_f<T>(to_f<T>(a[idx]) + to_f<T>(b[idx]));
 }
@@ -364,6 +371,7 @@ __global__ void add_kernel(const T *__restrict__ a, const T *__restrict__ b, T *
 template <typename TI, typename T>
 __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI *__restrict__ x, T *__restrict__ col, int B, int Cin, int xh,
                                                           int xw, int Ho, int Wo, int ksz, int stride, int pad, int ldcol) {
+  pdl_prologue();
   const int chunks = Cin * ksz;   // == ldcol / 8
   const int64_t total = (int64_t)B * Ho * Wo * chunks;
   const bool word_path = sizeof(TI) == 1 && (xw & 3) == 0 && ((stride * 1 - pad - 1) & 3) == 0 && (stride & 3) == 0 &&
@@ -411,6 +419,7 @@ __global__ void __launch_bounds__(256) im2col_nchw_kernel(const TI *__restrict__
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const T *__restrict__ x, T *__restrict__ col, int B, int Hi, int Wi,
                                                           int Cin, int Ho, int Wo, int ksz, int stride, int pad, int K, int ldcol) {
+  pdl_prologue();
   const int cchunks = Cin / 8, chunks = ldcol / 8;
   const int64_t total = (int64_t)B * Ho * Wo * chunks;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -440,6 +449,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const T *__restrict__ dcol, int ldcol, const T *__restrict__ dres,
                                                           T *__restrict__ dx, int B, int Hi, int Wi, int Cin, int Ho, int Wo, int ksz,
                                                           int stride, int pad) {
+  pdl_prologue();
   const int cchunks = Cin / 8;
   const int64_t total = (int64_t)B * Hi * Wi * cchunks;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -482,6 +492,7 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const T *__restrict__ 
 template <typename T>
 __global__ void prep_weight_kernel(const float *__restrict__ src, const float *__restrict__ scale, T *__restrict__ dst, int ldd,
                                    T *__restrict__ dstT, int lddT, int N, int K, int perm, int Cin, int ksz) {
+  pdl_prologue();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * K) return;
   const int n = (int)(idx / K), k = (int)(idx % K);
@@ -503,6 +514,7 @@ __global__ void prep_weight_kernel(const float *__restrict__ src, const float *_
 }
 
 __global__ void scaled_bias_kernel(const float *b, const float *scale, float *out, int N) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) out[i] = b[i] * scale[i];
 }
@@ -512,6 +524,7 @@ __global__ void scaled_bias_kernel(const float *b, const float *scale, float *ou
 __global__ void ls_finalize_kernel(float *__restrict__ G, float *__restrict__ s, const float *__restrict__ W,
                                    const float *__restrict__ b, const float *__restrict__ gamma, float *__restrict__ dW,
                                    float *__restrict__ db, float *__restrict__ dgamma, int N, int K) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -537,11 +550,13 @@ inline int blocks_for(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
 // engine and queue behind whatever bulk host->device upload is in flight there (the next step's input batch).
 __global__ void copy_u4_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int64_t n16, const unsigned char *__restrict__ src_tail,
                                unsigned char *__restrict__ dst_tail, int ntail) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n16) dst[i] = src[i];
   if (i < ntail) dst_tail[i] = src_tail[i];
 }
 __global__ void zero_u32_kernel(unsigned *__restrict__ p, int64_t n) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0u;
 }
@@ -563,14 +578,14 @@ int layernorm_fwd(int dtype, const void *x, const float *w, const float *b, void
   if (dtype == LEOD_BF16 && C % 8 == 0 && ((((uintptr_t)x) | ((uintptr_t)y) | ((uintptr_t)w) | ((uintptr_t)b)) & 15) == 0) {
     const int nchunk = C / 8;
 #define LN_FWD_FAST(LPR, NCH)                                                                                         \
-  ln_fwd_bf16_kernel<LPR, NCH><<<ceil_div(M, 8 * (32 / LPR)), 256, 0, st>>>((const bf16 *)x, w, b, (bf16 *)y, M, C, eps)
+  LEOD_LAUNCH((ln_fwd_bf16_kernel<LPR, NCH>), ceil_div(M, 8 * (32 / LPR)), 256, 0, st, (const bf16 *)x, w, b, (bf16 *)y, M, C, eps)
     if (nchunk <= 8) { LN_FWD_FAST(8, 1); } else if (nchunk <= 16) { LN_FWD_FAST(16, 1); } else if (nchunk <= 32) { LN_FWD_FAST(32, 1); }
     else { LN_FWD_FAST(32, 2); }
 #undef LN_FWD_FAST
     LEOD_LAUNCH_CHECK();
     return 0;
   }
-#define LN_FWD(NV) DISPATCH_T(dtype, (ln_fwd_kernel<T, NV><<<ceil_div(M, 8), 256, 0, st>>>((const T *)x, w, b, (T *)y, M, C, eps)))
+#define LN_FWD(NV) DISPATCH_T(dtype, (LEOD_LAUNCH((ln_fwd_kernel<T, NV>), ceil_div(M, 8), 256, 0, st, (const T *)x, w, b, (T *)y, M, C, eps)))
   const int nv = ceil_div(C, 32);
   if (nv <= 1) { LN_FWD(1); } else if (nv <= 2) { LN_FWD(2); } else if (nv <= 3) { LN_FWD(3); } else if (nv <= 4) { LN_FWD(4); }
   else if (nv <= 6) { LN_FWD(6); } else if (nv <= 8) { LN_FWD(8); } else if (nv <= 12) { LN_FWD(12); } else { LN_FWD(16); }
@@ -587,7 +602,7 @@ int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, cons
       ((((uintptr_t)x) | ((uintptr_t)dy) | ((uintptr_t)dres) | ((uintptr_t)dx)) & 15) == 0) {
     const int nchunk = C / 8;
 #define LN_BWD_FAST(LPR, NCH)                                                                                          \
-  ln_bwd_bf16_kernel<LPR, NCH><<<std::max(1, std::min(ceil_div(M, 8 * (32 / LPR)), 148 * 4)), 256, 0, st>>>(             \
+  LEOD_LAUNCH((ln_bwd_bf16_kernel<LPR, NCH>), std::max(1, std::min(ceil_div(M, 8 * (32 / LPR)), 148 * 4)), 256, 0, st, \
       (const bf16 *)x, w, (const bf16 *)dy, (const bf16 *)dres, (bf16 *)dx, dw, db, M, C, eps)
     if (nchunk <= 8) { LN_BWD_FAST(8, 1); } else if (nchunk <= 16) { LN_BWD_FAST(16, 1); } else if (nchunk <= 32) { LN_BWD_FAST(32, 1); }
     else { LN_BWD_FAST(32, 2); }
@@ -599,7 +614,7 @@ int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, cons
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
 #define LN_BWD(NV)                                                                                                             \
-  DISPATCH_T(dtype, (ln_bwd_kernel<T, NV><<<blocks, 256, 0, st>>>((const T *)x, w, (const T *)dy, (const T *)dres, (T *)dx, dw, db, \
+  DISPATCH_T(dtype, (LEOD_LAUNCH((ln_bwd_kernel<T, NV>), blocks, 256, 0, st, (const T *)x, w, (const T *)dy, (const T *)dres, (T *)dx, dw, db, \
                                                                   M, C, eps)))
   const int nv = ceil_div(C, 32);
   if (nv <= 1) { LN_BWD(1); } else if (nv <= 2) { LN_BWD(2); } else if (nv <= 3) { LN_BWD(3); } else if (nv <= 4) { LN_BWD(4); }
@@ -612,7 +627,7 @@ int layernorm_bwd(int dtype, const void *x, const float *w, const void *dy, cons
 int lstm_pointwise_fwd(int dtype, void *gates, const void *c_prev, void *h_out, void *c_out, int M, int C, cudaStream_t st) {
   ProfScope ps(PK_LSTM, 30.0 * M * C, 11.0 * M * C * dtype_size(dtype), st);
   const int64_t n = (int64_t)M * C;
-  DISPATCH_T(dtype, (lstm_fwd_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((T *)gates, (const T *)c_prev, (T *)h_out, (T *)c_out, M, C)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((lstm_fwd_kernel<T>), blocks_for(n, 256), 256, 0, st, (T *)gates, (const T *)c_prev, (T *)h_out, (T *)c_out, M, C)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -621,7 +636,7 @@ int lstm_pointwise_bwd(int dtype, const void *gates, const void *c_prev, const v
                        const void *dc, void *dgates, void *dc_prev, int M, int C, cudaStream_t st, const void *dh3) {
   ProfScope ps(PK_LSTM, 30.0 * M * C, 13.0 * M * C * dtype_size(dtype), st);
   const int64_t n = (int64_t)M * C;
-  DISPATCH_T(dtype, (lstm_bwd_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)gates, (const T *)c_prev, (const T *)c_out,
+  DISPATCH_T(dtype, (LEOD_LAUNCH((lstm_bwd_kernel<T>), blocks_for(n, 256), 256, 0, st, (const T *)gates, (const T *)c_prev, (const T *)c_out,
                                                                            (const T *)dh, (const T *)dh2, (const T *)dh3,
                                                                            (const T *)dc, (T *)dgates, (T *)dc_prev, M, C)));
   LEOD_LAUNCH_CHECK();
@@ -630,7 +645,7 @@ int lstm_pointwise_bwd(int dtype, const void *gates, const void *c_prev, const v
 
 int add_tensors(int dtype, const void *a, const void *b, void *out, int64_t n, cudaStream_t st) {
   ProfScope ps(PK_OTHER, 0.0, 3.0 * n * dtype_size(dtype), st);
-  DISPATCH_T(dtype, (add_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>((const T *)a, (const T *)b, (T *)out, n)));
+  DISPATCH_T(dtype, (LEOD_LAUNCH((add_kernel<T>), blocks_for(n, 256), 256, 0, st, (const T *)a, (const T *)b, (T *)out, n)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -644,7 +659,7 @@ int im2col_nchw(int x_dtype, int dtype, const void *x, void *col, int B, int Cin
   int nb = blocks_for(n, 256);
   if (nb > 148 * 32) nb = 148 * 32;
 #define IM2COL_CASE(TI)                                                                                                     \
-  DISPATCH_T(dtype, (im2col_nchw_kernel<TI, T><<<nb, 256, 0, st>>>((const TI *)x, (T *)col, B, Cin, xh, xw, Ho, Wo, ksz, stride, \
+  DISPATCH_T(dtype, (LEOD_LAUNCH((im2col_nchw_kernel<TI, T>), nb, 256, 0, st, (const TI *)x, (T *)col, B, Cin, xh, xw, Ho, Wo, ksz, stride, \
                                                                  pad, ldcol)))
   if (x_dtype == LEOD_U8) {
     IM2COL_CASE(uint8_t);
@@ -665,7 +680,7 @@ int im2col_nhwc(int dtype, const void *x, void *col, int B, int Hi, int Wi, int 
   const int K = Cin * ksz * ksz;
   LEOD_REQUIRE(Cin % 8 == 0 && ldcol % 8 == 0, "im2col_nhwc: Cin=%d / pitch %d must be multiples of 8", Cin, ldcol);
   const int64_t n = (int64_t)B * Ho * Wo * (ldcol / 8);
-  DISPATCH_T(dtype, (im2col_nhwc_kernel<T><<<std::min(blocks_for(n, 256), 148 * 16), 256, 0, st>>>((const T *)x, (T *)col, B, Hi, Wi, Cin, Ho, Wo, ksz,
+  DISPATCH_T(dtype, (LEOD_LAUNCH((im2col_nhwc_kernel<T>), std::min(blocks_for(n, 256), 148 * 16), 256, 0, st, (const T *)x, (T *)col, B, Hi, Wi, Cin, Ho, Wo, ksz,
                                                                               stride, pad, K, ldcol)));
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -677,7 +692,7 @@ int col2im_nhwc(int dtype, const void *dcol, int ldcol, const void *dres, void *
   const int Ho = (Hi + 2 * pad - ksz) / stride + 1, Wo = (Wi + 2 * pad - ksz) / stride + 1;
   LEOD_REQUIRE(Cin % 8 == 0 && ldcol % 8 == 0, "col2im_nhwc: Cin=%d / pitch %d must be multiples of 8", Cin, ldcol);
   const int64_t n = (int64_t)B * Hi * Wi * (Cin / 8);
-  DISPATCH_T(dtype, (col2im_nhwc_kernel<T><<<std::min(blocks_for(n, 256), 148 * 16), 256, 0, st>>>((const T *)dcol, ldcol, (const T *)dres, (T *)dx, B,
+  DISPATCH_T(dtype, (LEOD_LAUNCH((col2im_nhwc_kernel<T>), std::min(blocks_for(n, 256), 148 * 16), 256, 0, st, (const T *)dcol, ldcol, (const T *)dres, (T *)dx, B,
                                                                               Hi, Wi, Cin, Ho, Wo, ksz, stride, pad)));
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -686,21 +701,21 @@ int col2im_nhwc(int dtype, const void *dcol, int ldcol, const void *dres, void *
 int prep_weight(int dtype, const float *src, const float *scale, void *dst, int ldd, void *dstT, int lddT, int N, int K, int perm,
                 int Cin, int ksz, cudaStream_t st) {
   const int64_t n = (int64_t)N * K;
-  DISPATCH_T(dtype, (prep_weight_kernel<T><<<blocks_for(n, 256), 256, 0, st>>>(src, scale, (T *)dst, ldd, (T *)dstT, lddT, N, K, perm,
+  DISPATCH_T(dtype, (LEOD_LAUNCH((prep_weight_kernel<T>), blocks_for(n, 256), 256, 0, st, src, scale, (T *)dst, ldd, (T *)dstT, lddT, N, K, perm,
                                                                               Cin, ksz)));
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 
 int prep_scaled_bias(const float *b, const float *scale, float *out, int N, cudaStream_t st) {
-  scaled_bias_kernel<<<blocks_for(N, 128), 128, 0, st>>>(b, scale, out, N);
+  LEOD_LAUNCH((scaled_bias_kernel), blocks_for(N, 128), 128, 0, st, b, scale, out, N);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
 
 int layerscale_grad_finalize(const float *G, const float *s, const float *W, const float *b, const float *gamma, float *dW,
                              float *db, float *dgamma, int N, int K, cudaStream_t st) {
-  ls_finalize_kernel<<<ceil_div(N, 8), 256, 0, st>>>((float *)G, (float *)s, W, b, gamma, dW, db, dgamma, N, K);
+  LEOD_LAUNCH((ls_finalize_kernel), ceil_div(N, 8), 256, 0, st, (float *)G, (float *)s, W, b, gamma, dW, db, dgamma, N, K);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -713,7 +728,7 @@ int device_copy(void *dst, const void *src, size_t bytes, cudaStream_t st) {
   }
   const int64_t n16 = (int64_t)(bytes / 16);
   const int ntail = (int)(bytes % 16);
-  copy_u4_kernel<<<blocks_for(std::max<int64_t>(n16, ntail), 256), 256, 0, st>>>((const uint4 *)src, (uint4 *)dst, n16,
+  LEOD_LAUNCH((copy_u4_kernel), blocks_for(std::max<int64_t>(n16, ntail), 256), 256, 0, st, (const uint4 *)src, (uint4 *)dst, n16,
                                                                                 (const unsigned char *)src + n16 * 16,
                                                                                 (unsigned char *)dst + n16 * 16, ntail);
   LEOD_LAUNCH_CHECK();
@@ -722,7 +737,7 @@ int device_copy(void *dst, const void *src, size_t bytes, cudaStream_t st) {
 
 int device_zero_u32(unsigned *p, int64_t n, cudaStream_t st) {
   if (n <= 0) return 0;
-  zero_u32_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, n);
+  LEOD_LAUNCH((zero_u32_kernel), blocks_for(n, 256), 256, 0, st, p, n);
   LEOD_LAUNCH_CHECK();
   return 0;
 }

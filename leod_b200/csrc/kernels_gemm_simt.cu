@@ -33,6 +33,7 @@ __device__ __forceinline__ void epilogue_store(const GemmNT &g, int m, int n, fl
 
 template <typename T>
 __global__ void __launch_bounds__(NT) gemm_nt_simt_kernel(const GemmNT g) {
+  pdl_prologue();
   __shared__ float As[BK][BM + PADW];
   __shared__ float Bs[BK][BN + PADW];
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
@@ -89,6 +90,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT) gemm_tn_simt_kernel(const T *__restrict__ dY, int ldy, const T *__restrict__ X, int ldx,
                                                          float *__restrict__ dW, int ldw, float *__restrict__ dbias, int M,
                                                          int N, int K, int rows_per_split, const ConvTaps taps, int tiles_k) {
+  pdl_prologue();
   __shared__ float Ys[BK][BN + PADW];
   __shared__ float Xs[BK][BN + PADW];
   const int tid = threadIdx.x, ty = tid / 16, tx = tid % 16;
@@ -151,9 +153,9 @@ int gemm_nt_simt(int dtype, const GemmNT &g, cudaStream_t st) {
   if (g.M <= 0 || g.N <= 0) return 0;
   dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
   if (dtype == LEOD_F32)
-    gemm_nt_simt_kernel<float><<<grid, NT, 0, st>>>(g);
+    LEOD_LAUNCH((gemm_nt_simt_kernel<float>), grid, NT, 0, st, g);
   else
-    gemm_nt_simt_kernel<bf16><<<grid, NT, 0, st>>>(g);
+    LEOD_LAUNCH((gemm_nt_simt_kernel<bf16>), grid, NT, 0, st, g);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -173,9 +175,9 @@ int gemm_tn_simt(int dtype, const void *dY, int ldy, const void *X, int ldx, flo
   splits = ceil_div(M, rows);
   dim3 grid(tn, tk * ntap, splits);
   if (dtype == LEOD_F32)
-    gemm_tn_simt_kernel<float><<<grid, NT, 0, st>>>((const float *)dY, ldy, (const float *)X, ldx, dW, ldw, dbias, M, N, K, rows, tp, tk);
+    LEOD_LAUNCH((gemm_tn_simt_kernel<float>), grid, NT, 0, st, (const float *)dY, ldy, (const float *)X, ldx, dW, ldw, dbias, M, N, K, rows, tp, tk);
   else
-    gemm_tn_simt_kernel<bf16><<<grid, NT, 0, st>>>((const bf16 *)dY, ldy, (const bf16 *)X, ldx, dW, ldw, dbias, M, N, K, rows, tp, tk);
+    LEOD_LAUNCH((gemm_tn_simt_kernel<bf16>), grid, NT, 0, st, (const bf16 *)dY, ldy, (const bf16 *)X, ldx, dW, ldw, dbias, M, N, K, rows, tp, tk);
   LEOD_LAUNCH_CHECK();
   return 0;
 }

@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
                                                                     const __grid_constant__ CUtensorMap mapA2,
                                                                     const __grid_constant__ CUtensorMap mapB,
                                                                     const __grid_constant__ CUtensorMap mapB2, const NtArgs a) {
+  pdl_launch_dependents();   // the next kernel of the stream may start its own prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = a.BN * TILE_K * 2;
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // barriers, TMEM and tensor maps are set up: only now depend on the previous kernel's results
 
   if (warp == 0) {
     if (lane == 0) {
@@ -599,6 +601,7 @@ constexpr int TN_BOX_BYTES = 64 * 64 * 2;  // 64 tokens x 64 elements
 
 __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap mapY,
                                                                  const __grid_constant__ CUtensorMap mapX, const TnArgs a) {
+  pdl_launch_dependents();   // the next kernel of the stream may start its own prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int nbx = a.BKt / 64;                              // X boxes per stage
@@ -631,6 +634,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // barriers, TMEM and tensor maps are set up: only now depend on the previous kernel's results
 
   if (warp == 0) {
     if (lane == 0) {
@@ -712,6 +716,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
 // row) and walks down the rows with a stride chosen so that a warp reads consecutive chunks: fully coalesced, 4 loads
 // in flight per thread.  blockDim.x is a multiple of the chunks per row, so the chunk of a thread never changes.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16 *__restrict__ Y, int ldy, float *__restrict__ out, int M, int N) {
+  pdl_prologue();
   __shared__ float red[256][9];
   const int nc = N >> 3;
   const int tid = threadIdx.x;
@@ -750,6 +755,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16 *__restrict
 }
 // generic fallback (N not a multiple of 8 or more than 256 chunks per row)
 __global__ void colsum_bf16_slow_kernel(const bf16 *__restrict__ Y, int ldy, float *__restrict__ out, int M, int N, int rows_per_block) {
+  pdl_prologue();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
@@ -800,6 +806,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const __gri
                                                                       const __grid_constant__ CUtensorMap mapH0,  // h0 [C, M, 1]
                                                                       const __grid_constant__ CUtensorMap mapW,   // W_h [C, 4C]
                                                                       const LstmSeqArgs a) {
+  pdl_launch_dependents();   // the next kernel of the stream may start its own prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = 4 * a.CW * TILE_K * 2;
@@ -831,6 +838,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_fwd_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // barriers, TMEM and tensor maps are set up: only now depend on the previous kernel's results
 
   // work list of this CTA: split -> one (tile, pass); otherwise tiles blockIdx.x, +gridDim.x, ... with all passes
   const int tile_first = a.split ? (int)blockIdx.x / a.npass : (int)blockIdx.x;
@@ -1086,6 +1094,7 @@ constexpr int LB_WARP_STAGE = 8 * 4096;   // per gate-math warp: gates [4], c_pr
 __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap mapG,   // dgates [4C, M, L]
                                                                       const __grid_constant__ CUtensorMap mapW,   // W_h^T [4C, C]
                                                                       const LstmBwdArgs a) {
+  pdl_launch_dependents();   // the next kernel of the stream may start its own prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = a.CWb * TILE_K * 2;
@@ -1116,6 +1125,7 @@ __global__ void __launch_bounds__(LS_THREADS, 1) lstm_seq_bwd_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // barriers, TMEM and tensor maps are set up: only now depend on the previous kernel's results
 
   const int tile_first = a.split ? (int)blockIdx.x / a.npass : (int)blockIdx.x;
   const int tile_step = a.split ? a.tiles_m : (int)gridDim.x;
@@ -1435,15 +1445,15 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   const int grid = ceil_div(tiles, waves);
   const int threads = 64 + 32 * epi_warps;
   if (!a.staged) {
-    gemm_nt_tc_kernel<-1><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<-1>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
   } else if (g.epi == EPI_GELU) {
-    gemm_nt_tc_kernel<EPI_GELU><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_GELU>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
   } else if (g.epi == EPI_RESID) {
-    gemm_nt_tc_kernel<EPI_RESID><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_RESID>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
   } else if (g.epi == EPI_GELU_BWD) {
-    gemm_nt_tc_kernel<EPI_GELU_BWD><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_GELU_BWD>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
   } else {
-    gemm_nt_tc_kernel<EPI_NONE><<<grid, threads, smem, st>>>(mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_NONE>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
   }
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -1487,7 +1497,7 @@ int lstm_seq_fwd_tc(void *gates, const void *Wh, int ldw, const void *h0, const 
   }
   LEOD_TRY(device_zero_u32(flags, (int64_t)a.tiles_m * L, st));
   const int grid = a.split ? a.tiles_m * a.npass : std::min(a.tiles_m, num_sms());
-  lstm_seq_fwd_kernel<<<grid, LS_THREADS, smem, st>>>(mH, mH0, mW, a);
+  LEOD_LAUNCH((lstm_seq_fwd_kernel), grid, LS_THREADS, smem, st, mH, mH0, mW, a);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -1527,7 +1537,7 @@ int lstm_seq_bwd_tc(const void *gates, const void *c_all, const void *c0, const 
   }
   LEOD_TRY(device_zero_u32(flags, (int64_t)a.tiles_m * L, st));
   const int grid = a.split ? a.tiles_m * a.npass : std::min(a.tiles_m, num_sms());
-  lstm_seq_bwd_kernel<<<grid, LS_THREADS, smem, st>>>(mG, mW, a);
+  LEOD_LAUNCH((lstm_seq_bwd_kernel), grid, LS_THREADS, smem, st, mG, mW, a);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -1573,7 +1583,7 @@ int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int l
     attr_set = true;
   }
   dim3 grid(tn, tk * ntap, splits);
-  gemm_tn_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(mY, mX, a);
+  LEOD_LAUNCH((gemm_tn_tc_kernel), grid, NUM_THREADS, smem, st, mY, mX, a);
   LEOD_LAUNCH_CHECK();
   if (dbias) {
     const int nc = N / 8;
@@ -1581,11 +1591,11 @@ int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int l
       const int threads = 256 / nc * nc, rows_per_pass = threads / nc;
       int blocks = ceil_div(M, rows_per_pass * 4);
       if (blocks > 148 * 8) blocks = 148 * 8;
-      colsum_bf16_kernel<<<blocks, threads, 0, st>>>((const bf16 *)dY, ldy, dbias, M, N);
+      LEOD_LAUNCH((colsum_bf16_kernel), blocks, threads, 0, st, (const bf16 *)dY, ldy, dbias, M, N);
     } else {
       const int rpb = (int)round_up(ceil_div(M, 148 * 2), 32);
       dim3 g2(ceil_div(N, 128), ceil_div(M, rpb));
-      colsum_bf16_slow_kernel<<<g2, 128, 0, st>>>((const bf16 *)dY, ldy, dbias, M, N, rpb);
+      LEOD_LAUNCH((colsum_bf16_slow_kernel), g2, 128, 0, st, (const bf16 *)dY, ldy, dbias, M, N, rpb);
     }
     LEOD_LAUNCH_CHECK();
   }

@@ -10,6 +10,7 @@ namespace {
 __global__ void adamw_ema_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
                                  float *__restrict__ ema, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
                                  float clip, float step_size, float bc2_sqrt, float ema_alpha) {
+  pdl_prologue();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i];
     if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
@@ -33,7 +34,7 @@ extern "C" int leod_adamw_ema(float *p, const float *g, float *m, float *v, floa
   const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adamw_ema_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, clip_value,
+  LEOD_LAUNCH((adamw_ema_kernel), blocks, 256, 0, (cudaStream_t)stream, p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, clip_value,
                                                              (float)(lr / bc1), (float)sqrt(bc2), ema_alpha);
   LEOD_LAUNCH_CHECK();
   return 0;

@@ -84,6 +84,7 @@ __device__ __forceinline__ float match_cost(const Label &l, const float *t, int 
 __global__ void __launch_bounds__(256) head_decode_kernel(HeadPtrs rp, HeadGeom g, SimotaCfg cfg, float *__restrict__ preds, float *__restrict__ tout,
                                                          const float *__restrict__ labels, int nmax, uint8_t *__restrict__ flags,
                                                          int *__restrict__ match_cnt, int *__restrict__ match_gt) {
+  pdl_prologue();
   extern __shared__ float s_lab[];   // [nmax][4]: cx, cy, flags (1 nonzero | 2 valid), unused
   const int b = blockIdx.y;
   if (labels) {
@@ -157,6 +158,7 @@ __device__ __forceinline__ void block_arg(const float *arr, int n, float &val, i
 __global__ void __launch_bounds__(256) simota_match_kernel(HeadGeom g, SimotaCfg cfg, const float *__restrict__ tout, const float *__restrict__ labels,
                                                           int nmax, const uint8_t *__restrict__ flags, int *__restrict__ match_cnt,
                                                           int *__restrict__ match_gt) {
+  pdl_prologue();
   extern __shared__ float s_buf[];
   __shared__ float s_val[8];
   __shared__ int s_idx[8];
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__(256) simota_resolve_kernel(HeadGeom g, SimotaC
                                                             int nmax, const uint8_t *__restrict__ flags, const int *__restrict__ match_cnt,
                                                             const int *__restrict__ match_gt, int *__restrict__ assign, float *__restrict__ miou_out,
                                                             double *__restrict__ sums) {
+  pdl_prologue();
   extern __shared__ float s_lab[];   // [nmax][7] raw rows
   __shared__ float s_red[8][4];
   const int b = blockIdx.y;
@@ -296,6 +299,7 @@ __global__ void __launch_bounds__(256) simota_resolve_kernel(HeadGeom g, SimotaC
 
 // yolo_head.py:563-597: loss = reg_w * sum(1 - iou^2)/num_fg + obj_w * sum(bce_obj)/num_fg + cls_w * sum(bce_cls)/num_fg
 __global__ void loss_finalize_kernel(const double *__restrict__ sums, SimotaCfg cfg, float *__restrict__ out) {
+  pdl_prologue();
   const double nfg = fmax(sums[3], 1.0);
   const float li = (float)(cfg.reg_w * sums[0] / nfg), lo = (float)(cfg.obj_w * sums[1] / nfg), lc = (float)(cfg.cls_w * sums[2] / nfg);
   out[0] = li + lo + lc;
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(HeadGeom g, SimotaCfg cfg
                                                       const uint8_t *__restrict__ flags, const int *__restrict__ assign,
                                                       const float *__restrict__ miou_in, const double *__restrict__ sums,
                                                       const float *__restrict__ gscale, HeadGradPtrs dp) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= g.A) return;
@@ -343,6 +348,7 @@ __global__ void __launch_bounds__(256) loss_bwd_kernel(HeadGeom g, SimotaCfg cfg
 // [B, A, 8] fp32 <-> the padded-flat per-level raw-gradient matrices (diagnostics / custom losses)
 template <typename T, bool SET>
 __global__ void __launch_bounds__(256) raw_grad_copy_kernel(HeadGeom g, float *__restrict__ flat, HeadGradPtrs dp) {
+  pdl_prologue();
   const int b = blockIdx.y;
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= g.A) return;
@@ -362,11 +368,11 @@ __global__ void __launch_bounds__(256) raw_grad_copy_kernel(HeadGeom g, float *_
 int raw_grad_copy(int dtype, const HeadGeom &g, float *flat, const HeadGradPtrs &dp, int set, cudaStream_t st) {
   dim3 grid(ceil_div(g.A, 256), g.B);
   if (dtype == LEOD_F32) {
-    if (set) raw_grad_copy_kernel<float, true><<<grid, 256, 0, st>>>(g, flat, dp);
-    else raw_grad_copy_kernel<float, false><<<grid, 256, 0, st>>>(g, flat, dp);
+    if (set) LEOD_LAUNCH((raw_grad_copy_kernel<float, true>), grid, 256, 0, st, g, flat, dp);
+    else LEOD_LAUNCH((raw_grad_copy_kernel<float, false>), grid, 256, 0, st, g, flat, dp);
   } else {
-    if (set) raw_grad_copy_kernel<bf16, true><<<grid, 256, 0, st>>>(g, flat, dp);
-    else raw_grad_copy_kernel<bf16, false><<<grid, 256, 0, st>>>(g, flat, dp);
+    if (set) LEOD_LAUNCH((raw_grad_copy_kernel<bf16, true>), grid, 256, 0, st, g, flat, dp);
+    else LEOD_LAUNCH((raw_grad_copy_kernel<bf16, false>), grid, 256, 0, st, g, flat, dp);
   }
   LEOD_LAUNCH_CHECK();
   return 0;
@@ -378,7 +384,7 @@ int head_decode(const HeadPtrs &rp, const HeadGeom &g, const SimotaCfg &cfg, flo
   dim3 grid(ceil_div(g.A, 256), g.B);
   const size_t smem = tout ? (size_t)nmax * 4 * sizeof(float) : 0;
   LEOD_REQUIRE(smem <= 48 * 1024, "head_decode: %d labels per image exceed the shared-memory table", nmax);
-  head_decode_kernel<<<grid, 256, smem, st>>>(rp, g, cfg, preds, tout, tout ? labels : nullptr, nmax, flags, match_cnt, match_gt);
+  LEOD_LAUNCH((head_decode_kernel), grid, 256, smem, st, rp, g, cfg, preds, tout, tout ? labels : nullptr, nmax, flags, match_cnt, match_gt);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -394,12 +400,12 @@ int simota_loss_fwd(const HeadGeom &g, const SimotaCfg &cfg, const float *tout, 
     attr_set = true;
   }
   LEOD_REQUIRE(smem_m <= 200 * 1024, "simota: %d anchors exceed the shared-memory cost table", g.A);
-  simota_match_kernel<<<dim3(nmax, g.B), 256, smem_m, st>>>(g, cfg, tout, labels, nmax, flags, match_cnt, match_gt);
+  LEOD_LAUNCH((simota_match_kernel), dim3(nmax, g.B), 256, smem_m, st, g, cfg, tout, labels, nmax, flags, match_cnt, match_gt);
   LEOD_LAUNCH_CHECK();
-  simota_resolve_kernel<<<dim3(ceil_div(g.A, 256), g.B), 256, (size_t)nmax * 7 * sizeof(float), st>>>(g, cfg, tout, labels, nmax, flags, match_cnt,
+  LEOD_LAUNCH((simota_resolve_kernel), dim3(ceil_div(g.A, 256), g.B), 256, (size_t)nmax * 7 * sizeof(float), st, g, cfg, tout, labels, nmax, flags, match_cnt,
                                                                                                       match_gt, assign, miou, sums);
   LEOD_LAUNCH_CHECK();
-  loss_finalize_kernel<<<1, 1, 0, st>>>(sums, cfg, losses);
+  LEOD_LAUNCH((loss_finalize_kernel), 1, 1, 0, st, sums, cfg, losses);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -408,9 +414,9 @@ int simota_loss_bwd(int dtype, const HeadGeom &g, const SimotaCfg &cfg, const fl
                     const int *assign, const float *miou, const double *sums, const float *gscale, const HeadGradPtrs &dp, cudaStream_t st) {
   dim3 grid(ceil_div(g.A, 256), g.B);
   if (dtype == LEOD_F32)
-    loss_bwd_kernel<float><<<grid, 256, 0, st>>>(g, cfg, tout, labels, nmax, flags, assign, miou, sums, gscale, dp);
+    LEOD_LAUNCH((loss_bwd_kernel<float>), grid, 256, 0, st, g, cfg, tout, labels, nmax, flags, assign, miou, sums, gscale, dp);
   else
-    loss_bwd_kernel<bf16><<<grid, 256, 0, st>>>(g, cfg, tout, labels, nmax, flags, assign, miou, sums, gscale, dp);
+    LEOD_LAUNCH((loss_bwd_kernel<bf16>), grid, 256, 0, st, g, cfg, tout, labels, nmax, flags, assign, miou, sums, gscale, dp);
   LEOD_LAUNCH_CHECK();
   return 0;
 }

@@ -94,6 +94,7 @@ struct TrackArgs {
 // LinearTracker over one sequence in one direction (linear.py:196-292, pseudo_labeler.py:211-225).  Backward = frames in reverse
 // order with mirrored frame indices and the rows of every frame reversed (pseudo_labeler.py:286-296).
 __global__ void __launch_bounds__(32) track_seq_kernel(TrackArgs a) {
+  pdl_prologue();
   __shared__ Track tr[MAXT];
   __shared__ int order[MAXT];
   __shared__ float dets[64][5];
@@ -293,6 +294,7 @@ struct AssembleArgs {
 // EventSeqData._track_filter (pseudo_labeler.py:298-333): ignore labels, in-painted boxes appended to their frame (new frames where the
 // detector had nothing), frames in ascending order.
 __global__ void __launch_bounds__(32) track_assemble_kernel(AssembleArgs a) {
+  pdl_prologue();
   if (threadIdx.x != 0) return;
   const int s = blockIdx.x;
   const int f0 = a.seq_ptr[s], f1 = a.seq_ptr[s + 1];
@@ -349,6 +351,7 @@ __global__ void __launch_bounds__(32) track_assemble_kernel(AssembleArgs a) {
 // class_id u4 @24, class_confidence f4 @28, objectness f4 @32, 4 bytes padding); stride 36: the packed form numpy's concatenate
 // produces in EventSeqData._summarize (pseudo_labeler.py:179-199).
 __global__ void pack_bbox_kernel(const float *__restrict__ rows, int64_t n, unsigned char *__restrict__ out, int stride) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float *r = rows + i * 8;
@@ -403,7 +406,7 @@ extern "C" int leod_track_filter(const float *rows, const int32_t *frame_ptr, co
   a.qpow = qp;
   LEOD_CUDA(cudaMemcpyAsync(qp, qpow_host, (size_t)npow * 8, cudaMemcpyHostToDevice, st));
   LEOD_CUDA(cudaMemsetAsync(status, 0, (size_t)S * 4, st));
-  track_seq_kernel<<<dim3(S, use_backward ? 2 : 1), 32, 0, st>>>(a);
+  LEOD_LAUNCH((track_seq_kernel), dim3(S, use_backward ? 2 : 1), 32, 0, st, a);
   LEOD_LAUNCH_CHECK();
   AssembleArgs b;
   b.rows = rows; b.frame_ptr = frame_ptr; b.frame_idx = frame_idx; b.seq_ptr = seq_ptr; b.remove = a.remove; b.total_rows = (int)total_rows;
@@ -412,7 +415,7 @@ extern "C" int leod_track_filter(const float *rows, const int32_t *frame_ptr, co
   b.hole_cap = hole_cap; b.ignore_label = ignore_label;
   b.out_rows = out_rows; b.out_row_base = out_row_base; b.out_frame_idx = out_frame_idx; b.out_frame_start = out_frame_start;
   b.out_frame_base = out_frame_base; b.out_counts = out_counts;
-  track_assemble_kernel<<<S, 32, 0, st>>>(b);
+  LEOD_LAUNCH((track_assemble_kernel), S, 32, 0, st, b);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -421,7 +424,7 @@ extern "C" int leod_pack_bbox(const float *rows, int64_t n, void *out, int strid
   LEOD_REQUIRE(stride == 36 || stride == 40, "leod_pack_bbox: record stride %d (36 = packed, 40 = BBOX_DTYPE)", stride);
   if (n == 0) return 0;
   LEOD_REQUIRE(rows && out, "leod_pack_bbox: null operand");
-  pack_bbox_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(rows, n, (unsigned char *)out, stride);
+  LEOD_LAUNCH((pack_bbox_kernel), ceil_div(n, 256), 256, 0, (cudaStream_t)stream, rows, n, (unsigned char *)out, stride);
   LEOD_LAUNCH_CHECK();
   return 0;
 }

@@ -8,6 +8,7 @@ namespace {
 __global__ void voxel_scatter_kernel(const int32_t *__restrict__ x, const int32_t *__restrict__ y, const int32_t *__restrict__ p,
                                      const int64_t *__restrict__ t, int64_t n, int bins, int H, int W,
                                      unsigned int *__restrict__ cnt) {
+  pdl_prologue();
   const int64_t t0 = t[0], t1 = t[n - 1];
   const float denom = __ll2float_rn(max(t1 - t0, (int64_t)1));
   const float fb = (float)bins;
@@ -23,6 +24,7 @@ __global__ void voxel_scatter_kernel(const int32_t *__restrict__ x, const int32_
 
 __global__ void voxel_finalize_kernel(const unsigned int *__restrict__ cnt, uint8_t *__restrict__ out, int64_t total, int cutoff,
                                       int fastmode) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   unsigned int c = cnt[i];
@@ -57,10 +59,10 @@ extern "C" int leod_voxel_bin(const int32_t *x, const int32_t *y, const int32_t 
   if (n > 0) {
     int blocks = (int)((n + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    voxel_scatter_kernel<<<blocks, 256, 0, st>>>(x, y, p, t, n, bins, H, W, g_cnt);
+    LEOD_LAUNCH((voxel_scatter_kernel), blocks, 256, 0, st, x, y, p, t, n, bins, H, W, g_cnt);
     LEOD_LAUNCH_CHECK();
   }
-  voxel_finalize_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(g_cnt, out, total, cutoff, fastmode);
+  LEOD_LAUNCH((voxel_finalize_kernel), (int)((total + 255) / 256), 256, 0, st, g_cnt, out, total, cutoff, fastmode);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
