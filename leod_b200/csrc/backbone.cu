@@ -138,6 +138,19 @@ int gemm_tn(leod_backbone *h, const void *dY, int ldy, const void *X, int ldx, f
   return gemm_tn_simt(h->cfg.dtype, dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, st);
 }
 
+// The stem runs as an implicit GEMM (kernels_stem.cu: operand tiles built on chip from the uint8 event tensor, no patch matrix)
+// on the product path: bf16 + tensor-core GEMMs + uint8 input.  LEOD_IMPLICIT_STEM=0 restores the explicit patch matrix, which
+// also serves the fp32 / SIMT / float-input paths and frame sizes that are not multiples of the 8 x 16 pixel tile.
+bool implicit_stem(const leod_backbone *h, int s, const void *x, int x_dtype, int x_h, int x_w) {
+  static const int enabled = [] {
+    const char *e = getenv("LEOD_IMPLICIT_STEM");
+    return e ? atoi(e) : 1;
+  }();
+  if (!enabled || s != 0 || h->cfg.dtype != LEOD_BF16 || h->gemm_impl != 1 || x_dtype != LEOD_U8) return false;
+  const StageD &d = h->d[0];
+  return d.ksz == 7 && d.stride == 4 && d.pad == 3 && d.Kp == d.Cin * 56 && stem_implicit_supported(d.Cin, x_h, x_w, d.Ho, d.Wo, d.C, x);
+}
+
 GemmNT mk(const void *A, int lda, const void *B, int ldb, void *C, int ldc, int M, int N, int K, const float *bias = nullptr,
           int epi = EPI_NONE, const void *R = nullptr, int ldr = 0, void *aux = nullptr, int ldaux = 0) {
   GemmNT g;
@@ -303,10 +316,15 @@ int front_fwd(leod_backbone *h, int s, int64_t nimg, const void *in, int x_dtype
   // row indices are 32-bit in the kernels (element offsets are computed in 64 bits)
   LEOD_REQUIRE(M64 < (1LL << 31) - 1024, "stage %d: %lld rows exceed the 32-bit row indexing of the kernels", s, (long long)M64);
   const int M = (int)M64;
+  const bool implicit = implicit_stem(h, s, in, x_dtype, x_h, x_w);
+  if (implicit) {
+    ProfScope ps(PK_GEMM_NT, 2.0 * M * C * d.Kp, (double)nimg * d.Cin * x_h * x_w + e * ((double)C * d.Kp + (double)M * C), st, M, C, d.Kp);
+    LEOD_TRY(stem_fwd_tc((const uint8_t *)in, (int)nimg, d.Cin, x_h, x_w, d.Ho, d.Wo, C, w.WconvT, d.Kp, b.y0, st));
+  }
   // the stem's patch matrix of a whole BPTT window is kept for the weight-gradient GEMM (seq_col0, sequence mode)
   const bool keep = s == 0 && h->col0_live && h->seq_col0 && nimg == h->seq_col0_imgs;
   const int64_t chunk_imgs = keep ? nimg : std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
-  for (int64_t i0 = 0; i0 < nimg; i0 += chunk_imgs) {
+  for (int64_t i0 = 0; i0 < nimg && !implicit; i0 += chunk_imgs) {
     const int n = (int)std::min<int64_t>(chunk_imgs, nimg - i0);
     void *colp = keep ? h->seq_col0 : h->ws_col;
     if (s == 0) {
@@ -432,6 +450,10 @@ int stage_wgrads(leod_backbone *h, int s, int64_t nimg, const void *in, int x_dt
     }
   }
   if (!(parts & 2)) return 0;
+  if (implicit_stem(h, s, in, x_dtype, x_h, x_w)) {
+    ProfScope ps(PK_GEMM_TN, 2.0 * M * C * d.K, 2.0 * (double)nimg * d.Cin * x_h * x_w + 2.0 * e * (double)M * C + 8.0 * C * d.K, st, M, C, d.K);
+    return stem_wgrad_tc((const uint8_t *)in, (int)nimg, d.Cin, x_h, x_w, d.Ho, d.Wo, C, g.dy0, w.Gconv, d.K, st);
+  }
   const bool keep = s == 0 && h->col0_live && h->seq_col0 && nimg == h->seq_col0_imgs;   // patches still there from the forward pass
   const int64_t chunk_imgs = keep ? nimg : std::max<int64_t>(1, h->ws_col_elems / (rows_per_img * d.Kp));
   for (int64_t i0 = 0; i0 < nimg; i0 += chunk_imgs) {
@@ -624,6 +646,8 @@ extern "C" int leod_backbone_prepare(leod_backbone_t *h, void *stream) {
     const StageP &p = h->p[s];
     StageW &w = h->w[s];
     LEOD_TRY(prep_weight(dt, P + p.convw, nullptr, w.Wconv, d.Kp, w.WconvT, C, C, d.K, s == 0 ? 2 : 1, d.Cin, d.ksz, st));
+    // the stem has no input gradient, so its transposed copy is unused: it holds the FP16 copy the implicit-GEMM forward reads
+    if (s == 0 && dt == LEOD_BF16) LEOD_TRY(stem_weight_to_f16(w.Wconv, w.WconvT, (int64_t)C * d.Kp, st));
     for (int b = 0; b < 2; ++b) {
       const BlockP &q = p.blk[b];
       BlockW &bw = w.blk[b];
@@ -725,7 +749,10 @@ static int ensure_seq(leod_backbone *h, int B, int L) {
   {
     const StageD &d0 = h->d[0];
     const int64_t rows = (int64_t)B * L * d0.Ho * d0.Wo;
-    if (rows * d0.Kp < (1LL << 31) * 4 && rows < (1LL << 31) &&
+    // the product path gathers the stem's operands on chip (kernels_stem.cu): no patch matrix to keep
+    const char *env = getenv("LEOD_IMPLICIT_STEM");
+    const bool maybe_explicit = !(h->cfg.dtype == LEOD_BF16 && h->gemm_impl == 1) || (env && atoi(env) == 0) || d0.Ho % 8 != 0 || d0.Wo % 16 != 0;
+    if (maybe_explicit && rows * d0.Kp < (1LL << 31) * 4 && rows < (1LL << 31) &&
         cudaMalloc(&h->seq_col0, rows * d0.Kp * (int64_t)h->esz()) == cudaSuccess) {
       h->seq_col0_imgs = (int64_t)B * L;
     } else {

@@ -249,3 +249,9 @@ int simota_loss_fwd(const HeadGeom &g, const SimotaCfg &cfg, const float *tout, 
 int simota_loss_bwd(int dtype, const HeadGeom &g, const SimotaCfg &cfg, const float *tout, const float *labels, int nmax, const uint8_t *flags,
                     const int *assign, const float *miou, const double *sums, const float *gscale, const HeadGradPtrs &dp, cudaStream_t st);
 int raw_grad_copy(int dtype, const HeadGeom &g, float *flat, const HeadGradPtrs &dp, int set, cudaStream_t st);
+
+// ------------------------------------------------------------------ implicit-GEMM stem (kernels_stem.cu)
+bool stem_implicit_supported(int Cin, int xh, int xw, int Ho, int Wo, int C, const void *x);
+int stem_weight_to_f16(const void *W_bf16, void *W_f16, int64_t n, cudaStream_t st);
+int stem_fwd_tc(const uint8_t *x, int nimg, int Cin, int xh, int xw, int Ho, int Wo, int C, const void *W, int ldw, void *y, cudaStream_t st);
+int stem_wgrad_tc(const uint8_t *x, int nimg, int Cin, int xh, int xw, int Ho, int Wo, int C, const void *dY, float *dW, int ldw, cudaStream_t st);
