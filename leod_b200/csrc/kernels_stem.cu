@@ -21,8 +21,13 @@ namespace {
 
 constexpr int ST_THREADS = 448;
 constexpr int ST_BUILDERS = 256;
-constexpr int ROWS_IN = 35, PITCH_IN = 68, WORDS_IN = 17;   // input window: 8*4+3 rows, 16*4+4 bytes per row
+// input window of a tile: 8*4+3 rows; per row the 80 bytes x = tx*64-16 .. tx*64+63 (the left halo is 4 bytes, the window starts 16
+// bytes early so that every row is five 16-byte cp.async pieces; an 80-byte pitch also makes the builders' 32-bit reads conflict-free:
+// a warp covers two pixel rows = 4 window rows = 80 words apart = 16 banks)
+constexpr int ROWS_IN = 35, PITCH_IN = 80, SEGS_IN = 5, X_HALO = 12;
+constexpr int CH_BYTES = ROWS_IN * PITCH_IN;
 constexpr int A_TILE = 128 * 128;                            // 128 pixels x 64 bf16
+constexpr int MAX_CHUNKS = 256;                              // Cin <= 32: 224 (cin, ky) chunks + the padding of the last k-block
 
 struct StemArgs {
   const uint8_t *x;
@@ -31,101 +36,78 @@ struct StemArgs {
   int ldw;
   int nimg, Cin, xh, xw, Ho, Wo, C, BN;
   int tiles_y, tiles_x, num_tiles;
-  int nkb, stages, in_bytes;
+  int nkb, stages, stages_b, in_bytes;
 };
 
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, bool valid) {
-  const int sz = valid ? 4 : 0;   // src-size 0 -> zero fill
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+// byte offset of chunk ch = cin*7 + ky (8 consecutive input bytes per output pixel) inside the staged window
+struct ChunkTab { int v[MAX_CHUNKS]; };
+constexpr ChunkTab make_chunk_tab() {
+  ChunkTab t{};
+  for (int ch = 0; ch < MAX_CHUNKS; ++ch) t.v[ch] = ((ch / 7) * ROWS_IN + ch % 7) * PITCH_IN;
+  return t;
+}
+__constant__ ChunkTab c_chunk = make_chunk_tab();
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 -> zero fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void builders_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ST_BUILDERS) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
 
-// Stage the input window of `tile` (channels c0 .. c0+nc-1) into `buf`: [nc][35][68] bytes, zero outside the frame.
-// thread -> (column word, row group of 3 rows): no divisions or multiplications in the loops; 255 of the 256 builders take part.
-__device__ __forceinline__ void stage_input(const StemArgs &a, int tile, int c0, int nc, uint8_t *buf, int bt) {
-  const int col = bt % WORDS_IN, rg = bt / WORDS_IN;
-  if (rg >= 15) return;
+// Stage the input window of `tile` (channels c0 .. c0+nc-1) into the shared buffer at `buf` (shared-space address): [nc][35][80]
+// bytes, zero outside the frame.  One (row, 16-byte piece) per thread, 175 of the 256 builders, one cp.async per channel.
+__device__ __forceinline__ void stage_input(const StemArgs &a, int tile, int c0, int nc, uint32_t buf, int bt) {
+  if (bt >= ROWS_IN * SEGS_IN) return;
+  const int row = bt / SEGS_IN, seg = bt - row * SEGS_IN;
   const int per_img = a.tiles_y * a.tiles_x;
   const int img = tile / per_img, tr = tile - img * per_img;
   const int ty = tr / a.tiles_x, tx = tr - ty * a.tiles_x;
-  const int ix = tx * 64 - 4 + col * 4;
-  const bool xok = ix >= 0 && ix + 3 < a.xw;
-  const int plane = a.xh * a.xw;
-  bool ok[3];
-  int goff[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int row = rg + 15 * i, iy = ty * 32 - 3 + row;
-    ok[i] = xok && row < ROWS_IN && iy >= 0 && iy < a.xh;
-    goff[i] = ok[i] ? iy * a.xw + ix : 0;
-  }
-  const uint8_t *src = a.x + ((size_t)img * a.Cin + c0) * plane;
-  uint32_t dst = smem_u32(buf) + rg * PITCH_IN + col * 4;
-  for (int c = 0; c < nc; ++c, src += plane, dst += ROWS_IN * PITCH_IN) {
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-      if (rg + 15 * i < ROWS_IN) cp_async4(dst + 15 * i * PITCH_IN, src + goff[i], ok[i]);
-  }
+  const int ix = tx * 64 - 16 + seg * 16, iy = ty * 32 - 3 + row;
+  const bool ok = ix >= 0 && ix + 15 < a.xw && iy >= 0 && iy < a.xh;
+  const size_t plane = (size_t)a.xh * a.xw;
+  const uint8_t *src = a.x + ((size_t)img * a.Cin + c0) * plane + (ok ? iy * a.xw + ix : 0);
+  uint32_t dst = buf + row * PITCH_IN + seg * 16;
+#pragma unroll 4
+  for (int c = 0; c < nc; ++c, src += plane, dst += CH_BYTES) cp_async16(dst, src, ok);
 }
-// One 16-byte chunk (8 pixels of one (cin, ky) row) of pixel row r = (py, px) into the swizzle-128B tile: chunk c of row r at
-// physical chunk c ^ (r & 7).  F16 = true (forward): the operand is FP16 — counts 0..255 are exact, byte b -> half 0x6400 | b =
-// 1024 + b through one PRMT per pair, minus 1024 with one HSUB2 (the weights are then fed as FP16 copies of their bf16 values: both
-// operands of a kind::f16 MMA must have the same format).  F16 = false (weight gradient, whose other operand is a bf16 gradient
-// that could underflow FP16): integer -> float -> bf16, exact as well.
+// 8 consecutive input bytes (two words) -> one 16-byte chunk of the operand tile.
+// Forward: the operand is FP16 — counts 0..255 are exact, byte b -> half 0x6400 | b = 1024 + b through one PRMT per pair, minus 1024
+// with one HSUB2 (the weights are then fed as FP16 copies of their bf16 values: both operands of a kind::f16 MMA must have the same
+// format).  Weight gradient (its other operand is a bf16 gradient that could underflow FP16): byte b -> float 0x4B000000 | b =
+// 2^23 + b, minus 2^23 = b exactly, whose low 16 bits are zero, so the upper halves of two floats ARE the bf16 pair.
 __device__ __forceinline__ uint32_t bytes_to_half2(uint32_t w, uint32_t selector) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(0x64646464u), "r"(selector));
+  const uint32_t d = prmt(w, 0x64646464u, selector);
   const __half2 h = __hsub2(*reinterpret_cast<const __half2 *>(&d), __halves2half2(__ushort_as_half(0x6400), __ushort_as_half(0x6400)));
   return *reinterpret_cast<const uint32_t *>(&h);
 }
-__device__ __forceinline__ uint32_t bytes_to_bf162(uint32_t w, int shift) {
-  const __nv_bfloat162 v = __floats2bfloat162_rn((float)((w >> shift) & 0xffu), (float)((w >> (shift + 8)) & 0xffu));
-  return *reinterpret_cast<const uint32_t *>(&v);
+__device__ __forceinline__ uint32_t bytes_to_bf162(uint32_t w, uint32_t sel0, uint32_t sel1) {
+  const float f0 = __uint_as_float(prmt(w, 0x4B000000u, sel0)) - 8388608.0f;
+  const float f1 = __uint_as_float(prmt(w, 0x4B000000u, sel1)) - 8388608.0f;
+  return prmt(__float_as_uint(f0), __float_as_uint(f1), 0x7632u);
 }
 template <bool F16>
-__device__ __forceinline__ void build_chunk(const uint8_t *src, bool valid, uint8_t *dst) {
-  uint32_t w0 = 0, w1 = 0;
-  if (valid) {
-    w0 = reinterpret_cast<const uint32_t *>(src)[0];
-    w1 = reinterpret_cast<const uint32_t *>(src)[1];
-  }
-  uint4 v;
-  if (F16) {
-    v.x = bytes_to_half2(w0, 0x4140u); v.y = bytes_to_half2(w0, 0x4342u);
-    v.z = bytes_to_half2(w1, 0x4140u); v.w = bytes_to_half2(w1, 0x4342u);
-  } else {
-    v.x = bytes_to_bf162(w0, 0); v.y = bytes_to_bf162(w0, 16);
-    v.z = bytes_to_bf162(w1, 0); v.w = bytes_to_bf162(w1, 16);
-  }
-  *reinterpret_cast<uint4 *>(dst) = v;
+__device__ __forceinline__ void build_chunk(uint32_t w0, uint32_t w1, uint32_t dst) {
+  if (F16)
+    sts128(dst, bytes_to_half2(w0, 0x4140u), bytes_to_half2(w0, 0x4342u), bytes_to_half2(w1, 0x4140u), bytes_to_half2(w1, 0x4342u));
+  else
+    sts128(dst, bytes_to_bf162(w0, 0x7540u, 0x7541u), bytes_to_bf162(w0, 0x7542u, 0x7543u), bytes_to_bf162(w1, 0x7540u, 0x7541u),
+           bytes_to_bf162(w1, 0x7542u, 0x7543u));
 }
-// Per-thread walk over the patch chunks ch = 8*kb + c of successive k-blocks: (cin, ky) of chunk c advance by (1, 1) per k-block
-// (8 = 7 + 1), so the byte offset of the chunk's input row in the staged window moves by a constant, with a fix-up when ky wraps.
-struct ChunkWalk {
-  int off[4], ky[4];
-  __device__ __forceinline__ void init(int kb, int cbase, int c0, int py, int px) {
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const int ch = kb * 8 + cbase + cc;
-      const int cin = ch / 7;
-      ky[cc] = ch - cin * 7;
-      off[cc] = ((cin - c0) * ROWS_IN + py * 4 + ky[cc]) * PITCH_IN + px * 4;
-    }
-  }
-  __device__ __forceinline__ void next() {
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      ky[cc] += 1;
-      off[cc] += (ROWS_IN + 1) * PITCH_IN;
-      if (ky[cc] >= 7) {
-        ky[cc] -= 7;
-        off[cc] += (ROWS_IN - 7) * PITCH_IN;
-      }
-    }
-  }
-};
 // instruction descriptor of kind::f16 with A = B = FP16 (format 0), D = FP32
 __device__ __forceinline__ uint32_t idesc_f16(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -137,22 +119,29 @@ __global__ void bf16_to_f16_kernel(const bf16 *__restrict__ src, __half *__restr
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+// Two rings: the A tiles built on chip (16 KB each, `stages` deep) and the weight tiles fetched by TMA (BN x 128 B each, `stages_b`
+// deep — deeper, because a 6 KB weight tile is consumed in ~0.15 us while a TMA round trip takes ~1 us).
 __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const StemArgs a) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_bytes = a.BN * 128;
-  const int stage_bytes = A_TILE + b_bytes;
-  uint8_t *ring = smem;
-  uint8_t *inbuf = smem + (size_t)a.stages * stage_bytes;
+  uint8_t *ringA = smem;
+  uint8_t *ringB = ringA + (size_t)a.stages * A_TILE;
+  uint8_t *inbuf = ringB + (size_t)a.stages_b * b_bytes;
   uint64_t *bars = (uint64_t *)(inbuf + 2 * (size_t)a.in_bytes);
-  uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages, *tmem_empty = tmem_full + 2;
+  uint64_t *fullA = bars, *emptyA = fullA + a.stages, *fullB = emptyA + a.stages, *emptyB = fullB + a.stages_b;
+  uint64_t *tmem_full = emptyB + a.stages_b, *tmem_empty = tmem_full + 2;
   uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1 + ST_BUILDERS / 32);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+      mbar_init(smem_u32(&fullA[s]), ST_BUILDERS / 32);
+      mbar_init(smem_u32(&emptyA[s]), 1);
+    }
+    for (int s = 0; s < a.stages_b; ++s) {
+      mbar_init(smem_u32(&fullB[s]), 1);
+      mbar_init(smem_u32(&emptyB[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&tmem_full[b]), 1);
@@ -174,34 +163,39 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
 
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
-        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-          const int s = it % a.stages;
-          mbar_wait_relaxed(smem_u32(&empty_bar[s]), ((it / a.stages) & 1) ^ 1);
-          const uint32_t fb = smem_u32(&full_bar[s]);
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          mbar_wait_relaxed(smem_u32(&emptyB[s]), ph ^ 1, 64);
+          const uint32_t fb = smem_u32(&fullB[s]);
           mbar_expect_tx(fb, b_bytes);
-          tma_load_2d(smem_u32(ring + (size_t)s * stage_bytes + A_TILE), &mapW, fb, kb * 64, 0);
+          tma_load_2d(smem_u32(ringB + (size_t)s * b_bytes), &mapW, fb, kb * 64, 0);
+          if (++s == a.stages_b) { s = 0; ph ^= 1; }
         }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = idesc_f16(128, a.BN, 0, 0);
-      int it = 0, j = 0;
+      int sa = 0, sb = 0, j = 0;
+      uint32_t pa = 0, pb = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
         const int buf = j & 1;
-        mbar_wait_relaxed(smem_u32(&tmem_empty[buf]), ((j >> 1) & 1) ^ 1);
+        mbar_wait_relaxed(smem_u32(&tmem_empty[buf]), ((j >> 1) & 1) ^ 1, 32);
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * acc_cols);
-        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-          const int s = it % a.stages;
-          mbar_wait_relaxed(smem_u32(&full_bar[s]), (it / a.stages) & 1, 32);
+        for (int kb = 0; kb < a.nkb; ++kb) {
+          mbar_wait(smem_u32(&fullB[sb]), pb);
+          mbar_wait(smem_u32(&fullA[sa]), pa);
           tc_fence_after();
-          const uint32_t sa = smem_u32(ring + (size_t)s * stage_bytes), sb = sa + A_TILE;
-          const uint64_t adesc = make_desc(sa, 16, 1024), bdesc = make_desc(sb, 16, 1024);
+          const uint64_t adesc = make_desc(smem_u32(ringA + (size_t)sa * A_TILE), 16, 1024);
+          const uint64_t bdesc = make_desc(smem_u32(ringB + (size_t)sb * b_bytes), 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) tc_mma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          tc_commit(smem_u32(&empty_bar[s]));
+          tc_commit(smem_u32(&emptyA[sa]));
+          tc_commit(smem_u32(&emptyB[sb]));
+          if (++sa == a.stages) { sa = 0; pa ^= 1; }
+          if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
         }
         tc_commit(smem_u32(&tmem_full[buf]));
       }
@@ -217,7 +211,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
       const int img = tile / per_img, tr = tile - img * per_img;
       const int ty = tr / a.tiles_x, tx = tr - ty * a.tiles_x;
       const size_t m = ((size_t)img * a.Ho + ty * 8 + py) * a.Wo + tx * 16 + px;
-      mbar_wait_relaxed(smem_u32(&tmem_full[buf]), (j >> 1) & 1, 256);
+      mbar_wait_relaxed(smem_u32(&tmem_full[buf]), (j >> 1) & 1, 512);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * acc_cols);
       bf16 *dst = a.y + m * a.C;
@@ -241,35 +235,44 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
     }
   } else {
-    // builders: stage the next tile's input with cp.async, expand the current one into the A tiles of the ring
+    // builders: stage the next tile's input with cp.async, expand the current one into the A tiles of the ring.  Chunks beyond
+    // Cin*7 (the tail of the last k-block) read whatever follows the window in shared memory: finite FP16 values that meet the zero
+    // weights of the TMA out-of-bounds fill.
     const int bt = threadIdx.x - 6 * 32;
     const int r = bt & 127, half = bt >> 7, py = r >> 4, px = r & 15;
-    const int nch = a.Cin * 7;
-    int dsto[4];
+    const uint32_t in_s = smem_u32(inbuf), ring_s = smem_u32(ringA);
+    const uint32_t thread_off = (uint32_t)(py * 4 * PITCH_IN + X_HALO + px * 4);
+    uint32_t dsto[4];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) dsto[cc] = r * 128 + (((half * 4 + cc) ^ (r & 7)) << 4);
-    int it = 0, j = 0;
-    stage_input(a, blockIdx.x, 0, a.Cin, inbuf, bt);
+    for (int cc = 0; cc < 4; ++cc) dsto[cc] = (uint32_t)(r * 128 + (((half * 4 + cc) ^ (r & 7)) << 4));
+    int s = 0, j = 0;
+    uint32_t ph = 0;
+    stage_input(a, blockIdx.x, 0, a.Cin, in_s, bt);
     cp_async_commit();
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
       const int next = tile + gridDim.x;
-      if (next < a.num_tiles) stage_input(a, next, 0, a.Cin, inbuf + (size_t)((j + 1) & 1) * a.in_bytes, bt);
+      if (next < a.num_tiles) stage_input(a, next, 0, a.Cin, in_s + (uint32_t)(((j + 1) & 1) * a.in_bytes), bt);
       cp_async_commit();
       cp_async_wait<1>();
       builders_sync();                       // every builder's share of this tile's window has landed
-      const uint8_t *in = inbuf + (size_t)(j & 1) * a.in_bytes;
-      ChunkWalk cw;
-      cw.init(0, half * 4, 0, py, px);
-      for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-        const int s = it % a.stages;
-        mbar_wait(smem_u32(&empty_bar[s]), ((it / a.stages) & 1) ^ 1);
-        uint8_t *tileA = ring + (size_t)s * stage_bytes;
+      const uint32_t in = in_s + (uint32_t)((j & 1) * a.in_bytes) + thread_off;
+      const int *tab = c_chunk.v + half * 4;
+      for (int kb = 0; kb < a.nkb; ++kb, tab += 8) {
+        uint32_t w[8];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) build_chunk<true>(in + cw.off[cc], kb * 8 + half * 4 + cc < nch, tileA + dsto[cc]);
-        cw.next();
+        for (int cc = 0; cc < 4; ++cc) {     // the window is read-only here: load before waiting for the ring slot
+          const uint32_t p = in + (uint32_t)tab[cc];
+          w[2 * cc] = lds32(p);
+          w[2 * cc + 1] = lds32(p + 4);
+        }
+        mbar_wait(smem_u32(&emptyA[s]), ph ^ 1);
+        const uint32_t tileA = ring_s + (uint32_t)(s * A_TILE);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) build_chunk<true>(w[2 * cc], w[2 * cc + 1], tileA + dsto[cc]);
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+        if (lane == 0) mbar_arrive(smem_u32(&fullA[s]));
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
       builders_sync();                       // the window buffer may be overwritten by the tile after next
     }
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_wgrad_kernel(const __grid_
       int j = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
         const int d = j & 1;
-        mbar_wait_relaxed(smem_u32(&dy_empty[d]), ((j >> 1) & 1) ^ 1);
+        mbar_wait_relaxed(smem_u32(&dy_empty[d]), ((j >> 1) & 1) ^ 1, 256);
         const uint32_t fb = smem_u32(&dy_full[d]);
         mbar_expect_tx(fb, A_TILE);
         const int img = tile / per_img, tr = tile - img * per_img;
@@ -348,21 +351,22 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_wgrad_kernel(const __grid_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(128, a.BN, 1, 1);
-      int it = 0, j = 0;
+      int s = 0, j = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
         const int d = j & 1;
-        mbar_wait_relaxed(smem_u32(&dy_full[d]), (j >> 1) & 1, 32);
+        mbar_wait(smem_u32(&dy_full[d]), (j >> 1) & 1);
         tc_fence_after();
         const uint64_t bdesc = make_desc(smem_u32(dyb + (size_t)d * A_TILE), A_TILE, 1024);
-        for (int p = 0; p < npair; ++p, ++it) {
-          const int s = it % a.stages;
-          mbar_wait_relaxed(smem_u32(&full_bar[s]), (it / a.stages) & 1, 32);
+        for (int p = 0; p < npair; ++p) {
+          mbar_wait(smem_u32(&full_bar[s]), ph);
           tc_fence_after();
           const uint64_t adesc = make_desc(smem_u32(ring + (size_t)s * pair_bytes), A_TILE, 1024);
 #pragma unroll
           for (int k = 0; k < 8; ++k)            // 16 pixels per MMA = 16 rows of 128 B (>>4: +128)
             tc_mma_bf16(tmem_base + (uint32_t)(p * ACC), adesc + 128 * k, bdesc + 128 * k, idesc, (j | k) != 0);
           tc_commit(smem_u32(&empty_bar[s]));
+          if (++s == a.stages) { s = 0; ph ^= 1; }
         }
         tc_commit(smem_u32(&dy_empty[d]));
       }
@@ -371,7 +375,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_wgrad_kernel(const __grid_
   } else if (warp < 6) {
     if (any) {
       const int quarter = warp & 3;
-      mbar_wait_relaxed(smem_u32(tmem_full), 0, 1000);
+      mbar_wait_relaxed(smem_u32(tmem_full), 0, 2000);
       tc_fence_after();
       const int K = a.Cin * 56;
       for (int p = 0; p < npair; ++p) {
@@ -387,38 +391,43 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_wgrad_kernel(const __grid_
       }
     }
   } else {
+    // builders (see the forward kernel); accumulator rows k >= Cin*56 hold products with whatever follows the window and are dropped
+    // by the epilogue
     const int bt = threadIdx.x - 6 * 32;
     const int r = bt & 127, hf = bt >> 7, py = r >> 4, px = r & 15;
-    const int nch = a.Cin * 7;
-    int dsto[4];
+    const uint32_t in_s = smem_u32(inbuf), ring_s = smem_u32(ring);
+    const uint32_t thread_off = (uint32_t)(py * 4 * PITCH_IN + X_HALO + px * 4) - (uint32_t)(c0 * CH_BYTES);
+    uint32_t dsto[4];
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) dsto[cc] = r * 128 + (((hf * 4 + cc) ^ (r & 7)) << 4);
-    int it = 0, j = 0;
-    if (any) stage_input(a, blockIdx.x, c0, nc, inbuf, bt);
+    for (int cc = 0; cc < 4; ++cc) dsto[cc] = (uint32_t)(r * 128 + (((hf * 4 + cc) ^ (r & 7)) << 4));
+    int s = 0, j = 0;
+    uint32_t ph = 0;
+    if (any) stage_input(a, blockIdx.x, c0, nc, in_s, bt);
     cp_async_commit();
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
       const int next = tile + gridDim.x;
-      if (next < a.num_tiles) stage_input(a, next, c0, nc, inbuf + (size_t)((j + 1) & 1) * a.in_bytes, bt);
+      if (next < a.num_tiles) stage_input(a, next, c0, nc, in_s + (uint32_t)(((j + 1) & 1) * a.in_bytes), bt);
       cp_async_commit();
       cp_async_wait<1>();
       builders_sync();
-      const uint8_t *in = inbuf + (size_t)(j & 1) * a.in_bytes;
-      ChunkWalk cw;
-      cw.init(pair0 * 2, hf * 4, c0, py, px);
-      for (int p = 0; p < npair; ++p, ++it) {
-        const int s = it % a.stages;
-        mbar_wait(smem_u32(&empty_bar[s]), ((it / a.stages) & 1) ^ 1);
-        uint8_t *pairA = ring + (size_t)s * pair_bytes;
+      const uint32_t in = in_s + (uint32_t)((j & 1) * a.in_bytes) + thread_off;
+      const int *tab = c_chunk.v + pair0 * 16 + hf * 4;
+      for (int p = 0; p < npair; ++p, tab += 16) {
+        uint32_t w[16];
 #pragma unroll
-        for (int t2 = 0; t2 < 2; ++t2) {
-          const int kb = (pair0 + p) * 2 + t2;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) build_chunk<false>(in + cw.off[cc], kb * 8 + hf * 4 + cc < nch, pairA + t2 * A_TILE + dsto[cc]);
-          cw.next();
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t pa = in + (uint32_t)tab[(q >> 2) * 8 + (q & 3)];
+          w[2 * q] = lds32(pa);
+          w[2 * q + 1] = lds32(pa + 4);
         }
+        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+        const uint32_t pairA = ring_s + (uint32_t)(s * pair_bytes);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) build_chunk<false>(w[2 * q], w[2 * q + 1], pairA + (uint32_t)((q >> 2) * A_TILE) + dsto[q & 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
+        if (++s == a.stages) { s = 0; ph ^= 1; }
       }
       builders_sync();
     }
@@ -449,11 +458,49 @@ int fill_args(StemArgs *a, const uint8_t *x, int nimg, int Cin, int xh, int xw, 
   return 0;
 }
 
+
+
+constexpr int SMEM_BUDGET = 225 * 1024;
+constexpr int TAIL_SLACK = 4096;   // the chunks past Cin*7 read up to ~2.6 KB beyond the second window buffer
+
+// shared-memory plan of the forward kernel: A ring 3-4 deep, weight ring as deep as fits (<= 8)
+bool fwd_plan(StemArgs *a, size_t *smem) {
+  a->in_bytes = (int)round_up((int64_t)a->Cin * CH_BYTES, 128);
+  const int b_bytes = a->BN * 128;
+  const int64_t fixed = 2 * (int64_t)a->in_bytes + TAIL_SLACK + 1024 + 512;
+  for (int sa = 4; sa >= 2; --sa) {
+    const int64_t left = SMEM_BUDGET - fixed - (int64_t)sa * A_TILE;
+    const int sb = (int)std::min<int64_t>(8, left / b_bytes);
+    if (sb >= sa) {
+      a->stages = sa; a->stages_b = sb;
+      *smem = (size_t)(fixed + (int64_t)sa * A_TILE + (int64_t)sb * b_bytes);
+      return true;
+    }
+  }
+  return false;
+}
+bool wgrad_plan(StemArgs *a, size_t *smem) {
+  const int npair_all = (a->nkb + 1) / 2;
+  if ((npair_all + 1) / 2 * 64 > 512) return false;                       // TMEM accumulators
+  const int max_nc = std::min(a->Cin, ((npair_all + 1) / 2 * 16 + 6) / 7 + 1);
+  a->in_bytes = (int)round_up((int64_t)max_nc * CH_BYTES, 128);
+  const int64_t fixed = 2 * (int64_t)a->in_bytes + 2 * A_TILE + TAIL_SLACK + 1024 + 512;
+  a->stages = (int)std::min<int64_t>(3, (SMEM_BUDGET - fixed) / (2 * A_TILE));
+  a->stages_b = 0;
+  *smem = (size_t)(fixed + (int64_t)a->stages * 2 * A_TILE);
+  return a->stages >= 2;
+}
+
 }  // namespace
 
 bool stem_implicit_supported(int Cin, int xh, int xw, int Ho, int Wo, int C, const void *x) {
-  return Ho % 8 == 0 && Wo % 16 == 0 && (xw & 3) == 0 && (((uintptr_t)x) & 3) == 0 && C % 16 == 0 && C <= 64 && Cin * 7 >= 16 && Cin <= 32 &&
-         xh <= Ho * 4 && xw <= Wo * 4;
+  if (!(Ho % 8 == 0 && Wo % 16 == 0 && (xw & 15) == 0 && (((uintptr_t)x) & 15) == 0 && C % 16 == 0 && C <= 64 && Cin * 7 >= 16 && Cin <= 32 &&
+        xh <= Ho * 4 && xw <= Wo * 4))
+    return false;
+  StemArgs a;
+  size_t smem;
+  fill_args(&a, (const uint8_t *)x, 1, Cin, xh, xw, Ho, Wo, C);
+  return fwd_plan(&a, &smem) && wgrad_plan(&a, &smem);
 }
 
 // FP16 copy of the prepared (bf16-valued) stem weight for the forward kernel
@@ -468,13 +515,10 @@ int stem_fwd_tc(const uint8_t *x, int nimg, int Cin, int xh, int xw, int Ho, int
   StemArgs a;
   fill_args(&a, x, nimg, Cin, xh, xw, Ho, Wo, C);
   a.y = (bf16 *)y; a.dW = nullptr; a.ldw = 0;
-  a.in_bytes = (int)round_up((int64_t)Cin * ROWS_IN * PITCH_IN, 128);
-  const int stage_bytes = A_TILE + a.BN * 128;
-  a.stages = std::min(4, (int)((220 * 1024 - 2 * a.in_bytes - 2048) / stage_bytes));
-  LEOD_REQUIRE(a.stages >= 2, "stem_fwd_tc: shared memory (Cin %d)", Cin);
+  size_t smem = 0;
+  LEOD_REQUIRE(fwd_plan(&a, &smem), "stem_fwd_tc: shared memory (Cin %d)", Cin);
   CUtensorMap mW;
   LEOD_TRY(tc_make_map_2d(&mW, W, (uint64_t)Cin * 56, C, ldw, 64, a.BN));
-  const size_t smem = (size_t)a.stages * stage_bytes + 2 * (size_t)a.in_bytes + 1024 + (2 * a.stages + 4) * 8 + 64;
   static bool attr_set = false;
   if (!attr_set) {
     LEOD_CUDA(cudaFuncSetAttribute(stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
@@ -491,15 +535,10 @@ int stem_wgrad_tc(const uint8_t *x, int nimg, int Cin, int xh, int xw, int Ho, i
   StemArgs a;
   fill_args(&a, x, nimg, Cin, xh, xw, Ho, Wo, C);
   a.y = nullptr; a.dW = dW; a.ldw = ldw;
-  const int npair_all = (a.nkb + 1) / 2;
-  LEOD_REQUIRE((npair_all + 1) / 2 * 64 <= 512, "stem_wgrad_tc: %d k-blocks exceed the TMEM accumulators", a.nkb);
-  const int max_nc = std::min(Cin, ((npair_all + 1) / 2 * 16 + 6) / 7 + 1);
-  a.in_bytes = (int)round_up((int64_t)max_nc * ROWS_IN * PITCH_IN, 128);
-  a.stages = std::min(3, (int)((220 * 1024 - 2 * a.in_bytes - 2 * A_TILE - 2048) / (2 * A_TILE)));
-  LEOD_REQUIRE(a.stages >= 2, "stem_wgrad_tc: shared memory (Cin %d)", Cin);
+  size_t smem = 0;
+  LEOD_REQUIRE(wgrad_plan(&a, &smem), "stem_wgrad_tc: shared memory / TMEM (Cin %d)", Cin);
   CUtensorMap mDY;
   LEOD_TRY(tc_make_map_2d(&mDY, dY, C, (uint64_t)nimg * Ho * Wo, C, 64, 16));
-  const size_t smem = (size_t)a.stages * 2 * A_TILE + 2 * A_TILE + 2 * (size_t)a.in_bytes + 1024 + (2 * a.stages + 5) * 8 + 64;
   static bool attr_set = false;
   if (!attr_set) {
     LEOD_CUDA(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
