@@ -138,6 +138,18 @@ int leod_gemm_nt(int impl, int dtype, const void *A, int lda, const void *A2, in
 int leod_gemm_tn(int impl, int dtype, const void *dY, int ldy, const void *X, int ldx, float *dW, int ldw, float *dbias,
                  int M, int N, int K, void *stream);
 
+/* The stem convolution (maxvit.py:143-182: bias-free 7x7, stride 4, padding 3) applied to the dataloader's uint8 event tensor
+ * without a patch matrix (implicit GEMM: operand tiles are built on chip).  x [nimg, Cin, xh, xw] uint8; the frame may be smaller
+ * than 4*Ho x 4*Wo, the missing rows/columns are the zero padding of utils/padding.py:33-58.  Weights / weight gradients are in
+ * patch order: k = (cin*7 + ky)*8 + slot, slot 0 <-> a zero weight, slot 1+kx <-> W[c, cin, ky, kx].
+ *   fwd  : y[nimg*Ho*Wo, C] (bf16) = conv(x, W);  W_f16 [C, ldw >= Cin*56] IEEE half
+ *   wgrad: dW[C, ldw] (fp32) += dY[nimg*Ho*Wo, C]^T (bf16) * patches(x)
+ * Needs Ho % 8 == 0, Wo % 16 == 0, xw % 16 == 0, x 16-byte aligned, C % 16 == 0, C <= 64, 3 <= Cin <= 32 (else an error). */
+int leod_stem_conv_fwd(const void *x, int nimg, int Cin, int xh, int xw, int Ho, int Wo, int C, const void *W_f16, int ldw, void *y,
+                       void *stream);
+int leod_stem_conv_wgrad(const void *x, int nimg, int Cin, int xh, int xw, int Ho, int Wo, int C, const void *dY, float *dW, int ldw,
+                         void *stream);
+
 /* Window / grid multi-head attention over an NHWC token matrix (maxvit.py:273-304, 343-354 minus the
  * two Linear layers).  qkv [B*H*W, 3C] with per-head [q|k|v] column blocks; out [B*H*W, C]. */
 int leod_attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, int C, int dim_head, int ph, int pw,

@@ -64,6 +64,8 @@ def _declare(lib):
         'leod_backbone_seq_bwd': (I, [VP, VP, I, I, I, I, I, _VP4, _VP4, _VP4, _VP4, _VP4, _VP4, _VP4, VP]),
         'leod_gemm_nt': (I, [I, I, VP, I, VP, I, I, VP, I, VP, I, I, I, I, VP, I, VP, I, VP, I, VP]),
         'leod_gemm_tn': (I, [I, I, VP, I, VP, I, VP, I, VP, I, I, I, VP]),
+        'leod_stem_conv_fwd': (I, [VP, I, I, I, I, I, I, I, VP, I, VP, VP]),
+        'leod_stem_conv_wgrad': (I, [VP, I, I, I, I, I, I, I, VP, VP, I, VP]),
         'leod_attention_fwd': (I, [I, VP, VP, I, I, I, I, I, I, I, I, VP]),
         'leod_attention_bwd': (I, [I, VP, VP, VP, I, I, I, I, I, I, I, I, VP]),
         'leod_layernorm_fwd': (I, [I, VP, VP, VP, VP, I, I, F, VP]),
@@ -116,7 +118,7 @@ EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 
                     'leod_backbone_save_bytes', 'leod_backbone_reserve', 'leod_backbone_set_gemm_impl',
                     'leod_backbone_step_fwd', 'leod_backbone_step_bwd', 'leod_backbone_grads_finalize', 'leod_backbone_seq_arena_bytes',
                     'leod_backbone_seq_fwd', 'leod_backbone_seq_bwd', 'leod_gemm_nt',
-                    'leod_gemm_tn', 'leod_attention_fwd', 'leod_attention_bwd', 'leod_layernorm_fwd', 'leod_layernorm_bwd',
+                    'leod_gemm_tn', 'leod_stem_conv_fwd', 'leod_stem_conv_wgrad', 'leod_attention_fwd', 'leod_attention_bwd', 'leod_layernorm_fwd', 'leod_layernorm_bwd',
                     'leod_lstm_gates_fwd', 'leod_lstm_gates_bwd', 'leod_detect_create', 'leod_detect_layout_only', 'leod_detect_destroy',
                     'leod_detect_param_info', 'leod_detect_buffer_info', 'leod_detect_counter_info', 'leod_detect_param_count',
                     'leod_detect_buffer_count', 'leod_detect_counter_count', 'leod_detect_num_anchors', 'leod_detect_bind',

@@ -108,6 +108,21 @@ extern "C" int leod_gemm_tn(int impl, int dtype, const void *dY, int ldy, const 
   return gemm_tn_simt(dtype, dY, ldy, X, ldx, dW, ldw, dbias, M, N, K, (cudaStream_t)stream);
 }
 
+extern "C" int leod_stem_conv_fwd(const void *x, int nimg, int Cin, int xh, int xw, int Ho, int Wo, int C, const void *W_f16, int ldw,
+                                  void *y, void *stream) {
+  LEOD_REQUIRE(x && W_f16 && y, "leod_stem_conv_fwd: null operand");
+  LEOD_REQUIRE(stem_implicit_supported(Cin, xh, xw, Ho, Wo, C, x), "leod_stem_conv_fwd: unsupported geometry (Cin %d, %dx%d -> %dx%d, C %d)", Cin,
+               xh, xw, Ho, Wo, C);
+  return stem_fwd_tc((const uint8_t *)x, nimg, Cin, xh, xw, Ho, Wo, C, W_f16, ldw, y, (cudaStream_t)stream);
+}
+extern "C" int leod_stem_conv_wgrad(const void *x, int nimg, int Cin, int xh, int xw, int Ho, int Wo, int C, const void *dY, float *dW,
+                                    int ldw, void *stream) {
+  LEOD_REQUIRE(x && dY && dW, "leod_stem_conv_wgrad: null operand");
+  LEOD_REQUIRE(stem_implicit_supported(Cin, xh, xw, Ho, Wo, C, x), "leod_stem_conv_wgrad: unsupported geometry (Cin %d, %dx%d -> %dx%d, C %d)",
+               Cin, xh, xw, Ho, Wo, C);
+  return stem_wgrad_tc((const uint8_t *)x, nimg, Cin, xh, xw, Ho, Wo, C, dY, dW, ldw, (cudaStream_t)stream);
+}
+
 extern "C" int leod_attention_fwd(int dtype, const void *qkv, void *out, int B, int H, int W, int C, int dim_head, int ph, int pw,
                                   int window, void *stream) {
   LEOD_REQUIRE(qkv && out, "leod_attention_fwd: null operand");

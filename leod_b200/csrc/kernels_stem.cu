@@ -13,14 +13,17 @@
 //              and 11..19), so each stages only its channels.
 // Warps: 0 = TMA (weights / dY), 1 = MMA issuer, 2..5 = epilogue, 6..13 = input staging + operand builders.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace {
 
-constexpr int ST_THREADS = 448;
-constexpr int ST_BUILDERS = 256;
+// Warps: 0 = TMA, 1 = MMA issuer, 2..5 = epilogue, then G groups of four builder warps.  A builder warp is latency-bound (dependent
+// PRMT -> HSUB2 -> STS chains, the proxy fence), so the kernels want many of them: each group builds every G-th k-block (pair).
+constexpr int FWD_GROUPS = 4, WG_GROUPS = 3;
+constexpr int FWD_THREADS = 192 + FWD_GROUPS * 128, WG_THREADS = 192 + WG_GROUPS * 128;
 // input window of a tile: 8*4+3 rows; per row the 80 bytes x = tx*64-16 .. tx*64+63 (the left halo is 4 bytes, the window starts 16
 // bytes early so that every row is five 16-byte cp.async pieces; an 80-byte pitch also makes the builders' 32-bit reads conflict-free:
 // a warp covers two pixel rows = 4 window rows = 80 words apart = 16 banks)
@@ -37,6 +40,7 @@ struct StemArgs {
   int nimg, Cin, xh, xw, Ho, Wo, C, BN;
   int tiles_y, tiles_x, num_tiles;
   int nkb, stages, stages_b, in_bytes;
+  int dbg;          // LEOD_STEM_DEBUG bit mask (timing experiments only; results are wrong when set)
 };
 
 // byte offset of chunk ch = cin*7 + ky (8 consecutive input bytes per output pixel) inside the staged window
@@ -54,7 +58,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool v
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void builders_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ST_BUILDERS) : "memory"); }
+template <int G> __device__ __forceinline__ void builders_sync() { asm volatile("bar.sync 1, %0;" ::"n"(G * 128) : "memory"); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -70,7 +74,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 
 // Stage the input window of `tile` (channels c0 .. c0+nc-1) into the shared buffer at `buf` (shared-space address): [nc][35][80]
-// bytes, zero outside the frame.  One (row, 16-byte piece) per thread, 175 of the 256 builders, one cp.async per channel.
+// bytes, zero outside the frame.  One (row, 16-byte piece) per thread, the first 175 builders, one cp.async per channel.
 __device__ __forceinline__ void stage_input(const StemArgs &a, int tile, int c0, int nc, uint32_t buf, int bt) {
   if (bt >= ROWS_IN * SEGS_IN) return;
   const int row = bt / SEGS_IN, seg = bt - row * SEGS_IN;
@@ -121,7 +125,7 @@ __global__ void bf16_to_f16_kernel(const bf16 *__restrict__ src, __half *__restr
 // ------------------------------------------------------------------------------------------------ forward
 // Two rings: the A tiles built on chip (16 KB each, `stages` deep) and the weight tiles fetched by TMA (BN x 128 B each, `stages_b`
 // deep — deeper, because a 6 KB weight tile is consumed in ~0.15 us while a TMA round trip takes ~1 us).
-__global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const StemArgs a) {
+__global__ void __launch_bounds__(FWD_THREADS, 1) stem_fwd_kernel(const __grid_constant__ CUtensorMap mapW, const StemArgs a) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(smem_u32(&fullA[s]), ST_BUILDERS / 32);
+      mbar_init(smem_u32(&fullA[s]), 4);   // one builder group (4 warps) per k-block
       mbar_init(smem_u32(&emptyA[s]), 1);
     }
     for (int s = 0; s < a.stages_b; ++s) {
@@ -167,10 +171,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
         for (int kb = 0; kb < a.nkb; ++kb) {
-          mbar_wait_relaxed(smem_u32(&emptyB[s]), ph ^ 1, 64);
+          if (!(a.dbg & 128)) mbar_wait_relaxed(smem_u32(&emptyB[s]), ph ^ 1, 64);
           const uint32_t fb = smem_u32(&fullB[s]);
-          mbar_expect_tx(fb, b_bytes);
-          tma_load_2d(smem_u32(ringB + (size_t)s * b_bytes), &mapW, fb, kb * 64, 0);
+          if (a.dbg & 4) {
+            mbar_arrive(fb);
+          } else {
+            mbar_expect_tx(fb, b_bytes);
+            tma_load_2d(smem_u32(ringB + (size_t)s * b_bytes), &mapW, fb, kb * 64, 0);
+          }
           if (++s == a.stages_b) { s = 0; ph ^= 1; }
         }
     }
@@ -191,9 +199,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
           const uint64_t adesc = make_desc(smem_u32(ringA + (size_t)sa * A_TILE), 16, 1024);
           const uint64_t bdesc = make_desc(smem_u32(ringB + (size_t)sb * b_bytes), 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          tc_commit(smem_u32(&emptyA[sa]));
-          tc_commit(smem_u32(&emptyB[sb]));
+          for (int k = 0; k < 4; ++k)
+            if (!(a.dbg & 2)) tc_mma_bf16(acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          if (!(a.dbg & 256)) tc_commit(smem_u32(&emptyA[sa]));
+          if (!(a.dbg & 128)) tc_commit(smem_u32(&emptyB[sb]));
           if (++sa == a.stages) { sa = 0; pa ^= 1; }
           if (++sb == a.stages_b) { sb = 0; pb ^= 1; }
         }
@@ -217,7 +226,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
       bf16 *dst = a.y + m * a.C;
       for (int c = 0; c < a.BN; c += 16) {
         uint32_t rr[16];
-        tmem_ld16(trow + (uint32_t)c, rr);
+        if (!(a.dbg & 512)) tmem_ld16(trow + (uint32_t)c, rr);
         uint4 o[2];
         uint32_t *ow = reinterpret_cast<uint32_t *>(o);
 #pragma unroll
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
           const __nv_bfloat162 pr = __floats2bfloat162_rn(__uint_as_float(rr[2 * q]), __uint_as_float(rr[2 * q + 1]));
           ow[q] = *reinterpret_cast<const uint32_t *>(&pr);
         }
-        if (c + 16 <= a.C) {
+        if (c + 16 <= a.C && !(a.dbg & 32)) {
           reinterpret_cast<uint4 *>(dst + c)[0] = o[0];
           reinterpret_cast<uint4 *>(dst + c)[1] = o[1];
         }
@@ -235,46 +244,53 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
     }
   } else {
-    // builders: stage the next tile's input with cp.async, expand the current one into the A tiles of the ring.  Chunks beyond
-    // Cin*7 (the tail of the last k-block) read whatever follows the window in shared memory: finite FP16 values that meet the zero
-    // weights of the TMA out-of-bounds fill.
+    // builders: stage the next tile's input with cp.async, expand the current one into the A tiles of the ring.  Group g builds the
+    // k-blocks whose running index is g modulo FWD_GROUPS (a thread builds the whole 128-byte row of its pixel), so that many k-blocks
+    // are in flight and the store -> proxy fence -> arrive chain of one overlaps the loads and conversions of the others.  Chunks beyond Cin*7 (the tail
+    // of the last k-block) read whatever follows the window in shared memory: finite FP16 values that meet the zero weights of the
+    // TMA out-of-bounds fill.
     const int bt = threadIdx.x - 6 * 32;
-    const int r = bt & 127, half = bt >> 7, py = r >> 4, px = r & 15;
+    const int r = bt & 127, grp = bt >> 7, py = r >> 4, px = r & 15;
     const uint32_t in_s = smem_u32(inbuf), ring_s = smem_u32(ringA);
     const uint32_t thread_off = (uint32_t)(py * 4 * PITCH_IN + X_HALO + px * 4);
-    uint32_t dsto[4];
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) dsto[cc] = (uint32_t)(r * 128 + (((half * 4 + cc) ^ (r & 7)) << 4));
-    int s = 0, j = 0;
-    uint32_t ph = 0;
+    const uint32_t row_off = (uint32_t)(r * 128), sw = (uint32_t)(r & 7);
+    int s = grp % a.stages, j = 0, it0 = 0;   // it0: running index of the tile's first k-block
+    uint32_t ph = (uint32_t)(grp / a.stages) & 1u;
     stage_input(a, blockIdx.x, 0, a.Cin, in_s, bt);
     cp_async_commit();
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j, it0 += a.nkb) {
       const int next = tile + gridDim.x;
-      if (next < a.num_tiles) stage_input(a, next, 0, a.Cin, in_s + (uint32_t)(((j + 1) & 1) * a.in_bytes), bt);
+      if (next < a.num_tiles && !(a.dbg & 16)) stage_input(a, next, 0, a.Cin, in_s + (uint32_t)(((j + 1) & 1) * a.in_bytes), bt);
       cp_async_commit();
       cp_async_wait<1>();
-      builders_sync();                       // every builder's share of this tile's window has landed
+      builders_sync<FWD_GROUPS>();           // every builder's share of this tile's window has landed
       const uint32_t in = in_s + (uint32_t)((j & 1) * a.in_bytes) + thread_off;
-      const int *tab = c_chunk.v + half * 4;
-      for (int kb = 0; kb < a.nkb; ++kb, tab += 8) {
-        uint32_t w[8];
+      for (int kb = (grp - it0) & (FWD_GROUPS - 1); kb < a.nkb; kb += FWD_GROUPS) {
+        const int *tab = c_chunk.v + kb * 8;
+        uint32_t w[16];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {     // the window is read-only here: load before waiting for the ring slot
+        for (int cc = 0; cc < 8; ++cc) {     // the window is read-only here: load before waiting for the ring slot
           const uint32_t p = in + (uint32_t)tab[cc];
-          w[2 * cc] = lds32(p);
-          w[2 * cc + 1] = lds32(p + 4);
+          if (a.dbg & 64) {
+            w[2 * cc] = p; w[2 * cc + 1] = p;
+          } else {
+            w[2 * cc] = lds32(p);
+            w[2 * cc + 1] = lds32(p + 4);
+          }
         }
-        mbar_wait(smem_u32(&emptyA[s]), ph ^ 1);
-        const uint32_t tileA = ring_s + (uint32_t)(s * A_TILE);
+        if (!(a.dbg & 256)) mbar_wait(smem_u32(&emptyA[s]), ph ^ 1);
+        const uint32_t rowA = ring_s + (uint32_t)(s * A_TILE) + row_off;
+        if (!(a.dbg & 1)) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) build_chunk<true>(w[2 * cc], w[2 * cc + 1], tileA + dsto[cc]);
-        fence_proxy_async_smem();
+          for (int cc = 0; cc < 8; ++cc) build_chunk<true>(w[2 * cc], w[2 * cc + 1], rowA + (((uint32_t)cc ^ sw) << 4));
+        }
+        if (!(a.dbg & 8)) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&fullA[s]));
-        if (++s == a.stages) { s = 0; ph ^= 1; }
+        s += FWD_GROUPS;
+        while (s >= a.stages) { s -= a.stages; ph ^= 1; }
       }
-      builders_sync();                       // the window buffer may be overwritten by the tile after next
+      builders_sync<FWD_GROUPS>();           // the window buffer may be overwritten by the tile after next
     }
   }
   tc_fence_before();
@@ -287,7 +303,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_fwd_kernel(const __grid_co
 
 // ------------------------------------------------------------------------------------------------ weight gradient
 // blockIdx.y = k half: 0 -> k-block pairs 0..4 (channels 0..11), 1 -> pairs 5..8 (channels 11..19).  dW[c, k] += sum_px dY[px, c] * patch[px, k].
-__global__ void __launch_bounds__(ST_THREADS, 1) stem_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const StemArgs a) {
+__global__ void __launch_bounds__(WG_THREADS, 1) stem_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const StemArgs a) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -308,7 +324,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_wgrad_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), ST_BUILDERS / 32);
+      mbar_init(smem_u32(&full_bar[s]), 4);   // one builder group (4 warps) per k-block pair
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -391,45 +407,51 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_wgrad_kernel(const __grid_
       }
     }
   } else {
-    // builders (see the forward kernel); accumulator rows k >= Cin*56 hold products with whatever follows the window and are dropped
-    // by the epilogue
+    // builders (see the forward kernel: the two groups build alternate k-block PAIRS); accumulator rows k >= Cin*56 hold products
+    // with whatever follows the window and are dropped by the epilogue
     const int bt = threadIdx.x - 6 * 32;
-    const int r = bt & 127, hf = bt >> 7, py = r >> 4, px = r & 15;
+    const int r = bt & 127, grp = bt >> 7, py = r >> 4, px = r & 15;
     const uint32_t in_s = smem_u32(inbuf), ring_s = smem_u32(ring);
     const uint32_t thread_off = (uint32_t)(py * 4 * PITCH_IN + X_HALO + px * 4) - (uint32_t)(c0 * CH_BYTES);
-    uint32_t dsto[4];
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) dsto[cc] = (uint32_t)(r * 128 + (((hf * 4 + cc) ^ (r & 7)) << 4));
-    int s = 0, j = 0;
-    uint32_t ph = 0;
+    const uint32_t row_off = (uint32_t)(r * 128), sw = (uint32_t)(r & 7);
+    int s = grp % a.stages, j = 0, it0 = 0;
+    uint32_t ph = (uint32_t)(grp / a.stages) & 1u;
     if (any) stage_input(a, blockIdx.x, c0, nc, in_s, bt);
     cp_async_commit();
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j) {
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++j, it0 += npair) {
       const int next = tile + gridDim.x;
       if (next < a.num_tiles) stage_input(a, next, c0, nc, in_s + (uint32_t)(((j + 1) & 1) * a.in_bytes), bt);
       cp_async_commit();
       cp_async_wait<1>();
-      builders_sync();
+      builders_sync<WG_GROUPS>();
       const uint32_t in = in_s + (uint32_t)((j & 1) * a.in_bytes) + thread_off;
-      const int *tab = c_chunk.v + pair0 * 16 + hf * 4;
-      for (int p = 0; p < npair; ++p, tab += 16) {
-        uint32_t w[16];
+      for (int p = (grp + WG_GROUPS - it0 % WG_GROUPS) % WG_GROUPS; p < npair; p += WG_GROUPS) {
+        const int *tab = c_chunk.v + (pair0 + p) * 16;
+        const uint32_t rowA = ring_s + (uint32_t)(s * pair_bytes) + row_off;
+        bool waited = false;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const uint32_t pa = in + (uint32_t)tab[(q >> 2) * 8 + (q & 3)];
-          w[2 * q] = lds32(pa);
-          w[2 * q + 1] = lds32(pa + 4);
+        for (int t2 = 0; t2 < 2; ++t2) {
+          uint32_t w[16];
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const uint32_t pa = in + (uint32_t)tab[t2 * 8 + cc];
+            w[2 * cc] = lds32(pa);
+            w[2 * cc + 1] = lds32(pa + 4);
+          }
+          if (!waited) {
+            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+            waited = true;
+          }
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) build_chunk<false>(w[2 * cc], w[2 * cc + 1], rowA + (uint32_t)(t2 * A_TILE) + (((uint32_t)cc ^ sw) << 4));
         }
-        mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-        const uint32_t pairA = ring_s + (uint32_t)(s * pair_bytes);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) build_chunk<false>(w[2 * q], w[2 * q + 1], pairA + (uint32_t)((q >> 2) * A_TILE) + dsto[q & 3]);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&full_bar[s]));
-        if (++s == a.stages) { s = 0; ph ^= 1; }
+        s += WG_GROUPS;
+        while (s >= a.stages) { s -= a.stages; ph ^= 1; }
       }
-      builders_sync();
+      builders_sync<WG_GROUPS>();
     }
   }
   tc_fence_before();
@@ -455,6 +477,12 @@ int fill_args(StemArgs *a, const uint8_t *x, int nimg, int Cin, int xh, int xw, 
   a->tiles_y = Ho / 8; a->tiles_x = Wo / 16;
   a->num_tiles = nimg * a->tiles_y * a->tiles_x;
   a->nkb = ceil_div(Cin * 56, 64);
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char *e = getenv("LEOD_STEM_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  a->dbg = dbg;
   return 0;
 }
 
@@ -525,7 +553,7 @@ int stem_fwd_tc(const uint8_t *x, int nimg, int Cin, int xh, int xw, int Ho, int
     attr_set = true;
   }
   const int waves = ceil_div(a.num_tiles, num_sms_());
-  LEOD_LAUNCH((stem_fwd_kernel), ceil_div(a.num_tiles, waves), ST_THREADS, smem, st, mW, a);
+  LEOD_LAUNCH((stem_fwd_kernel), ceil_div(a.num_tiles, waves), FWD_THREADS, smem, st, mW, a);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
@@ -545,7 +573,7 @@ int stem_wgrad_tc(const uint8_t *x, int nimg, int Cin, int xh, int xw, int Ho, i
     attr_set = true;
   }
   const int per_half = std::max(1, std::min(a.num_tiles, num_sms_() / 2));
-  LEOD_LAUNCH((stem_wgrad_kernel), dim3(per_half, 2), ST_THREADS, smem, st, mDY, a);
+  LEOD_LAUNCH((stem_wgrad_kernel), dim3(per_half, 2), WG_THREADS, smem, st, mDY, a);
   LEOD_LAUNCH_CHECK();
   return 0;
 }
