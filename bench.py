@@ -526,7 +526,8 @@ def run_train(args, wl, rank, local_rank, world):
                 copied[slot][c].record(cs)
     for c in consumed:
         c.record()
-    e2e_batches = [[make_batch(wl, dev_buf[s], host[j][1], resident[j][2]) for j in range(n_batches)] for s in range(2)]
+    # labels, index lists and the first-sample mask are HOST tensors here; the step uploads them itself (leod_upload_small)
+    e2e_batches = [[make_batch(wl, dev_buf[s], host[j][1], host[j][2]) for j in range(n_batches)] for s in range(2)]
     lag = max(0, args.e2e_lag)
     NLAG = lag + 1
     loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(NLAG)]

@@ -293,6 +293,39 @@ int leod_track_filter(const float *rows, const int32_t *frame_ptr, const int32_t
  * stride 40 = the declared dtype, 36 = the packed form EventSeqData._summarize (modules/pseudo_labeler.py:179-199) stores. */
 int leod_pack_bbox(const float *rows, int64_t n, void *out, int stride, void *stream);
 
+/* ------------------------------------------------------------------ input side: small uploads, augmentation
+ * leod_upload_small: host->device copy of a small tensor (label rows, index lists, first-sample masks) done by an SM kernel that reads
+ * the PINNED host buffer through its device mapping, so it never queues on the copy engine behind a bulk batch upload.  The host
+ * buffer must stay valid until the stream has passed this point.  Replaces the `.to(device)` calls of modules/detection.py:134-147,
+ * 226-236 (labels / selected indices) inside the step. */
+int leod_upload_small(void *dst, const void *src_pinned_host, int64_t nbytes, void *stream);
+
+/* Augmentation state of ONE sequence of the batch (data/utils/augmentor.py:26-60 AugmentationState after randomize_augmentation /
+ * _zoom_in_and_rescale chose the window; rotation has probability 0 in every shipped config and is not supported).
+ * The integer fields drive the event-tensor gather, the fp32 fields are the constants of the label arithmetic exactly as torch
+ * rounds the reference's Python doubles when they meet a float32 tensor. */
+typedef struct leod_augm_state {
+  int32_t h_flip;           /* apply_h_flip (augmentor.py:404-410, th.flip over x) */
+  int32_t t_flip;           /* DataType.IS_REVERSED (sequence_base.py:208-225): frames reversed in time AND channels reversed */
+  int32_t zoom_mode;        /* 0 none, 1 zoom-in (augmentor.py:310-330), 2 zoom-out (:228-247) */
+  int32_t x0, y0;           /* top-left corner of the zoom window */
+  int32_t win_h, win_w;     /* int(H / factor), int(W / factor) */
+  float flip_c;             /* W - 1 (labels.py:499-502) */
+  float lo_x, hi_x, lo_y, hi_y; /* zoom-in clamp window z_x0, z_x1 - 1, z_y0, z_y1 - 1 (labels.py:389-397) */
+  float mul;                /* scale_ multiplier (labels.py:482-497): zoom_in_factor, or 1 / zoom_out_factor */
+  float cap_x, cap_y;       /* new_img_wd - 1, new_img_ht - 1 of that scale_ call */
+} leod_augm_state;
+#define LEOD_AUGM_MAX_SEQ 32   /* sequences per launch (larger batches are processed in several launches) */
+
+/* in/out: device uint8 [L, B, C, H, W] (the loader's layout, data/utils/types.py EV_REPR stacked over time), out != in.
+ * states: HOST array of B records.  hflip -> zoom-in | zoom-out in the reference's order (augmentor.py:457-478) plus the time flip,
+ * nearest-exact resampling bit-identical to torch.nn.functional.interpolate(mode='nearest-exact'). */
+int leod_augment_ev_repr(const void *in, void *out, int L, int B, int C, int H, int W, const leod_augm_state *states, void *stream);
+/* rows: device fp32 [n, 8] ObjectLabels rows (t, x, y, w, h, cls, cls_conf, obj), transformed IN PLACE; row_seq: device int32 [n]
+ * batch index of each row; keep: device uint8 [n], 0 = removed by remove_flat_labels_ (labels.py:67-69).  Bit-identical to
+ * ObjectLabels.flip_lr_ / zoom_in_and_rescale_ / zoom_out_and_rescale_ (labels.py:371-411, 437-459, 482-502). */
+int leod_augment_labels(float *rows, const int32_t *row_seq, int64_t n, int B, const leod_augm_state *states, uint8_t *keep, void *stream);
+
 /* ------------------------------------------------------------------ event binning
  * Replaces data/utils/representations.py:78-123 (StackedHistogram.construct).
  * x,y,p: device int32 [n]; t: device int64 [n] (sorted); out: device uint8 [2*bins, H, W].

@@ -28,6 +28,13 @@ class DetectCfg(Structure):
                 ('reg_weight', c_float), ('obj_weight', c_float), ('cls_weight', c_float)]
 
 
+class AugmState(Structure):
+    """leod_augm_state (include/leod_b200.h): augmentation state of one sequence of the batch."""
+    _fields_ = [('h_flip', c_int32), ('t_flip', c_int32), ('zoom_mode', c_int32), ('x0', c_int32), ('y0', c_int32),
+                ('win_h', c_int32), ('win_w', c_int32), ('flip_c', c_float), ('lo_x', c_float), ('hi_x', c_float),
+                ('lo_y', c_float), ('hi_y', c_float), ('mul', c_float), ('cap_x', c_float), ('cap_y', c_float)]
+
+
 # int fn(void *ctx, double *buf, int64_t n, void *stream): sum buf over the ranks (leod_detect_set_allreduce)
 ALLREDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_int64, c_void_p)
 
@@ -101,6 +108,9 @@ def _declare(lib):
         'leod_track_filter': (I, [VP, VP, VP, VP, VP, c_int64, I, I, POINTER(ctypes.c_double), I, ctypes.c_double, ctypes.c_double, F, I, I, I, F, I,
                                   VP, VP, VP, VP, VP, VP, VP, VP, VP]),
         'leod_pack_bbox': (I, [VP, c_int64, VP, I, VP]),
+        'leod_upload_small': (I, [VP, VP, c_int64, VP]),
+        'leod_augment_ev_repr': (I, [VP, VP, I, I, I, I, I, POINTER(AugmState), VP]),
+        'leod_augment_labels': (I, [VP, VP, c_int64, I, POINTER(AugmState), VP, VP]),
         'leod_voxel_bin': (I, [VP, VP, VP, VP, c_int64, I, I, I, I, I, VP, VP]),
         'leod_adamw_ema': (I, [VP, VP, VP, VP, VP, c_int64, I, F, F, F, F, F, F, F, VP]),
     }
@@ -124,7 +134,7 @@ EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 
                     'leod_detect_buffer_count', 'leod_detect_counter_count', 'leod_detect_num_anchors', 'leod_detect_bind',
                     'leod_detect_prepare', 'leod_detect_reserve', 'leod_detect_set_allreduce', 'leod_fpn_head_fwd',
                     'leod_simota_loss_fwd', 'leod_simota_loss_bwd', 'leod_simota_assignment', 'leod_detect_get_raw', 'leod_detect_get_raw_grad', 'leod_detect_set_raw_grad', 'leod_fpn_head_bwd', 'leod_postprocess', 'leod_pred2label', 'leod_tta_merge', 'leod_track_workspace_bytes', 'leod_track_filter', 'leod_pack_bbox',
-                    'leod_voxel_bin', 'leod_adamw_ema']
+                    'leod_upload_small', 'leod_augment_ev_repr', 'leod_augment_labels', 'leod_voxel_bin', 'leod_adamw_ema']
 
 
 def lib():
@@ -149,6 +159,54 @@ def check(rc, what=''):
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else c_void_p(t.data_ptr())
+
+
+class _Staging:
+    """Ring of pinned host buffers for leod_upload_small.  A slot is reused only after the stream has passed the upload that read
+    it (one event per slot; with 16 slots the wait never blocks in practice)."""
+    SLOTS, SLOT_BYTES = 16, 1 << 18
+
+    def __init__(self):
+        self.buf = [torch.empty(self.SLOT_BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.SLOTS)]
+        self.ev = [None] * self.SLOTS
+        self.keep = [None] * self.SLOTS
+        self.next = 0
+
+    def acquire(self):
+        i = self.next
+        self.next = (i + 1) % self.SLOTS
+        if self.ev[i] is not None:
+            self.ev[i].synchronize()
+        return i
+
+
+_staging = None
+
+
+def upload_small(t: torch.Tensor, device) -> torch.Tensor:
+    """Host tensor (a few KB: label rows, index lists, masks) -> new device tensor, enqueued on the current stream as an SM
+    kernel (leod_upload_small), never on a copy engine.  The host is not blocked."""
+    global _staging
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    padded = (nbytes + 3) // 4 * 4
+    dst = torch.empty(max(padded, 4), dtype=torch.uint8, device=device)
+    out = dst[:nbytes].view(t.dtype).view(t.shape)
+    if nbytes == 0:
+        return out
+    if _staging is None:
+        _staging = _Staging()
+    slot = _staging.acquire()
+    # larger than a slot: a private pinned buffer, kept alive by the slot's bookkeeping until the slot is reused
+    host = _staging.buf[slot] if padded <= _Staging.SLOT_BYTES else torch.empty(padded, dtype=torch.uint8).pin_memory()
+    host[:nbytes].copy_(t.view(-1).view(torch.uint8))
+    with torch.cuda.device(dst.device):
+        check(lib().leod_upload_small(ptr(dst), c_void_p(host.data_ptr()), padded, stream_ptr(dst.device)), 'upload_small')
+        ev = torch.cuda.Event()
+        ev.record()
+    _staging.ev[slot] = ev
+    _staging.keep[slot] = host
+    return out
 
 
 def stream_ptr(device=None):

@@ -26,11 +26,13 @@ except Exception:  # noqa: BLE001
 
 
 def _h2d_async(t: torch.Tensor, device) -> torch.Tensor:
-    """Small host tensor -> device through pinned memory, without blocking the host on the stream's pending work (a
-    pageable copy is host-synchronous and would serialise the host behind the previous training step)."""
+    """Small host tensor -> device without blocking the host and without touching the copy engines (leod_upload_small: an SM
+    kernel reads a pinned staging buffer).  A cudaMemcpyAsync here would queue behind the input pipeline's bulk upload of the
+    next batch on the host->device engine and stall the compute stream at the start of every step."""
     if t.is_cuda or torch.device(device).type != 'cuda':
         return t.to(device)
-    return t.pin_memory().to(device, non_blocking=True)
+    from leod_b200 import _lib
+    return _lib.upload_small(t, device)
 
 
 def get_subsample_label_idx(L: int, use_every: int = -1, remove_every: int = -1):

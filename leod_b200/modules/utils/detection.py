@@ -86,7 +86,25 @@ class RNNStates:
 
     def reset(self, worker_id: int, indices_or_bool_tensor: Optional[Union[List[int], th.Tensor]] = None):
         if worker_id in self.states:
-            self.states[worker_id] = self.recursive_reset(self.states[worker_id], indices_or_bool_tensor)
+            idx = indices_or_bool_tensor
+            if th.is_tensor(idx) and idx.dtype == th.bool and not idx.is_cuda:
+                dev = self._first_device(self.states[worker_id])
+                if dev is not None and dev.type == 'cuda':      # one upload for all state tensors, off the copy engines
+                    from leod_b200 import _lib
+                    idx = _lib.upload_small(idx, dev)
+            self.states[worker_id] = self.recursive_reset(self.states[worker_id], idx)
+
+    @classmethod
+    def _first_device(cls, inp):
+        if isinstance(inp, th.Tensor):
+            return inp.device
+        if isinstance(inp, dict):
+            inp = list(inp.values())
+        for x in inp or ():
+            d = cls._first_device(x)
+            if d is not None:
+                return d
+        return None
 
 
 class SeqLens:

@@ -414,6 +414,55 @@ def gen_fullsize():
     np.savez_compressed(os.path.join(HERE, 'fullsize_cases.npz'), **out)
 
 
+def gen_augment():
+    """data/utils/augmentor.py run as a dataloader worker runs it (one RandomSpatialAugmentorGenX per sample, seeded torch RNG):
+    per case the sampled state, the augmented event frames and the augmented label rows.  Also the time flip of
+    sequence_base.py:208-225.  Inputs are regenerated by the tests from the stored seeds (tests/helpers.py: augment_inputs)."""
+    import zlib
+    from data.utils.augmentor import RandomSpatialAugmentorGenX
+    from data.utils.types import DataType
+    from data.genx_utils.labels import ObjectLabels, SparselyBatchedObjectLabels
+    import types
+    for name in ('torchdata.datapipes', 'torchdata.datapipes.map'):   # torchdata 0.11 dropped datapipes; only the base class name is needed
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['torchdata.datapipes.map'].MapDataPipe = object
+    from data.genx_utils.sequence_base import SequenceBase
+    sys.path[:0] = [os.path.join(HERE, '..'), os.path.join(HERE, '..', '..')]
+    from helpers import AUGMENT_CASES, AUGM_CFG, augment_inputs
+    out = {}
+    for ci, (H, W, L, C, seed, tflip, store) in enumerate(AUGMENT_CASES):
+        ev, label_rows = augment_inputs(H, W, L, C, seed)
+        aug = RandomSpatialAugmentorGenX(dataset_hw=(H, W), automatic_randomization=False, augm_config=DictConfig(AUGM_CFG))
+        torch.manual_seed(seed)
+        aug.randomize_augmentation()
+        aug.augm_state.apply_t_flip = False       # consumed by the dataset (dataset_rnd.py:102-113); the case's `tflip` plays that role
+        data = {DataType.EV_REPR: [torch.from_numpy(e.copy()) for e in ev],
+                DataType.OBJLABELS_SEQ: SparselyBatchedObjectLabels(
+                    [None if r is None else ObjectLabels(torch.from_numpy(r.copy()), (H, W)) for r in label_rows]),
+                DataType.IS_FIRST_SAMPLE: True, DataType.IS_PADDED_MASK: [False] * L, DataType.EV_IDX: list(range(L)),
+                DataType.IS_REVERSED: bool(tflip)}
+        if tflip:
+            data = SequenceBase.time_flip_data(data)
+        data = aug(data)
+        st = data[DataType.AUGM_STATE].to_dict()
+        out[f'{ci}/state'] = np.array([st['h_flip']['active'], st['zoom_in']['active'], st['zoom_in']['x0'], st['zoom_in']['y0'],
+                                       st['zoom_out']['active'], st['zoom_out']['x0'], st['zoom_out']['y0']], np.int64)
+        out[f'{ci}/factors'] = np.array([st['zoom_in']['factor'], st['zoom_out']['factor']], np.float64)
+        res = torch.stack(data[DataType.EV_REPR]).numpy()
+        out[f'{ci}/crc'] = np.int64(zlib.crc32(res.tobytes()))
+        out[f'{ci}/nnz'] = np.int64((res != 0).sum())
+        if store:
+            out[f'{ci}/ev'] = res
+        for t, lab in enumerate(data[DataType.OBJLABELS_SEQ]):
+            if lab is not None:
+                out[f'{ci}/label{t}'] = lab.object_labels.numpy()
+        print(ci, (H, W), 'tflip', tflip, st)
+    out['n'] = np.int64(len(AUGMENT_CASES))
+    np.savez_compressed(os.path.join(HERE, 'augment_cases.npz'), **out)
+    print('augment_cases.npz')
+
+
 if __name__ == '__main__':
     torch.set_num_threads(4)
     gen_net()
@@ -423,3 +472,4 @@ if __name__ == '__main__':
     gen_optim()
     gen_tracking()
     gen_fullsize()
+    gen_augment()

@@ -71,3 +71,32 @@ def canon_rows(d):
     score = d[:, 4] * d[:, 5]
     order = np.lexsort((d[:, 3], d[:, 2], d[:, 1], d[:, 0], d[:, 6], -score))
     return d[order]
+
+
+# ---- augmentation cases (tests/golden/augment_cases.npz): (H, W, L, C, seed, time flip, store the full output in the fixture)
+AUGM_CFG = dict(prob_hflip=0.5, prob_tflip=0.0, rotate=dict(prob=0, min_angle_deg=2, max_angle_deg=6),
+                zoom=dict(prob=0.8, zoom_in=dict(weight=8, factor=dict(min=1, max=1.5)),
+                          zoom_out=dict(weight=2, factor=dict(min=1, max=1.2))))     # config/dataset/base.yaml:19-39 (random sampling)
+AUGMENT_CASES = [(48, 64, 3, 4, s, s % 3 == 0, True) for s in range(1, 11)] + \
+                [(45, 50, 2, 3, s, s % 2 == 0, True) for s in range(11, 17)] + \
+                [(240, 304, 2, 20, s, s == 22, False) for s in range(20, 26)] + \
+                [(360, 640, 2, 20, s, False, False) for s in range(30, 34)]
+
+
+def augment_inputs(H, W, L, C, seed):
+    """-> (ev uint8 [L, C, H, W] numpy, L-list of label rows fp32 [n, 8] or None); the last frame always has boxes."""
+    rng = np.random.default_rng(1000 + seed)
+    ev = ((rng.random((L, C, H, W)) < 0.15) * rng.integers(1, 256, (L, C, H, W))).astype(np.uint8)
+    labels = []
+    for t in range(L):
+        if t < L - 1 and rng.random() < 0.4:
+            labels.append(None)
+            continue
+        n = int(rng.integers(1, 6))
+        w = rng.uniform(3, W * 0.5, n)
+        h = rng.uniform(3, H * 0.5, n)
+        x = rng.uniform(0, W - 1 - w)
+        y = rng.uniform(0, H - 1 - h)
+        rows = np.stack((np.full(n, 1000.0 + t), x, y, w, h, rng.integers(0, 2, n).astype(np.float64), np.ones(n), np.ones(n)), 1)
+        labels.append(rows.astype(np.float32))
+    return ev, labels

@@ -1,6 +1,6 @@
 """Summarise a --profile-csv file: per (kind, shape) launches, total/avg time, achieved GB/s and TFLOP/s."""
 import collections, sys
-KINDS = ['gemm_nt', 'gemm_tn', 'attention_fwd', 'attention_bwd', 'layernorm', 'lstm_gates', 'patch', 'other']
+KINDS = ['gemm_nt', 'gemm_tn', 'attention_fwd', 'attention_bwd', 'layernorm', 'lstm_gates', 'patch', 'other', 'conv']
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
 for line in open(sys.argv[1]):
     k, us, fl, by, d0, d1, d2 = line.strip().split(',')
