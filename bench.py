@@ -579,8 +579,8 @@ def run_train(args, wl, rank, local_rank, world):
         lib.leod_profile_csv(None)
         roof = roofline_from_kinds(kinds, args)
 
-    if rank == 0 and args.phases:
-        phase_report(torch, module, student, opt, batches, n_batches)
+    if args.phases:      # every rank runs the steps (they contain collectives); rank 0 prints
+        phase_report(torch, module, student, opt, batches, n_batches, quiet=rank != 0)
 
     ref_gpu, cpu = None, None
     if rank == 0 and world == 1 and not args.no_reference_gpu:
@@ -620,7 +620,7 @@ def run_train(args, wl, rank, local_rank, world):
         os._exit(0)     # NCCL teardown must never hang the driver's run
 
 
-def phase_report(torch, module, student, opt, batches, n_batches):
+def phase_report(torch, module, student, opt, batches, n_batches, quiet=False):
     marks = []
 
     def mark(name):
@@ -657,7 +657,8 @@ def phase_report(torch, module, student, opt, batches, n_batches):
             acc[n1] = acc.get(n1, 0.0) + e0_.elapsed_time(e1_) / 3
     bb.forward_sequence, student.mdl.forward_detect = o1, o2
     for k, v in acc.items():
-        print(f'  phase {k:28s} {v:8.3f} ms', file=sys.stderr)
+        if not quiet:
+            print(f'  phase {k:28s} {v:8.3f} ms', file=sys.stderr)
 
 
 # ----------------------------------------------------------------------------------------------- product arm: teacher sweep
@@ -722,8 +723,27 @@ def run_sweep(args, rank, local_rank, world):
     frames = world * 2 * SB * L * args.steps
     barrier()
     e0.record()
+    # end to end: every step's chunk comes from pinned host memory (uploaded on a copy stream while the previous chunk computes, as
+    # a prefetching loader does) and every step's labels are read back on the host before the next step is enqueued
+    cs = torch.cuda.Stream()
+    dev_buf = [torch.empty_like(resident[0]) for _ in range(2)]
+    up_done = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_upload(i):
+        with torch.cuda.stream(cs):
+            cs.wait_event(free[i % 2])
+            dev_buf[i % 2].copy_(host[i % 3], non_blocking=True)
+            up_done[i % 2].record(cs)
+    for f in free:
+        f.record()
+    issue_upload(0)
     for i in range(args.steps):
-        out = pl.predict_step(batch_of(host[i % 3].to(dev, non_blocking=True), False))
+        if i + 1 < args.steps:
+            issue_upload(i + 1)
+        torch.cuda.current_stream().wait_event(up_done[i % 2])
+        out = pl.predict_step(batch_of(dev_buf[i % 2], False))
+        free[i % 2].record()
         n_boxes = sum(len(l) for row in out[0] for l in row if l is not None)    # labels read back on the host
     e1.record()
     barrier()

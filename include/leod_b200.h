@@ -326,6 +326,24 @@ int leod_augment_ev_repr(const void *in, void *out, int L, int B, int C, int H, 
  * ObjectLabels.flip_lr_ / zoom_in_and_rescale_ / zoom_out_and_rescale_ (labels.py:371-411, 437-459, 482-502). */
 int leod_augment_labels(float *rows, const int32_t *row_seq, int64_t n, int B, const leod_augm_state *states, uint8_t *keep, void *stream);
 
+/* ------------------------------------------------------------------ evaluation
+ * Prophesee box filter + COCO bounding-box evaluation of per-frame buffers, replacing evaluate_list
+ * (utils/evaluation/prophesee/evaluation.py:5-42) -> filter_boxes (io/box_filtering.py:18-36) -> evaluate_detection
+ * (metrics/coco_eval.py:32-120) -> pycocotools COCOeval.evaluate()/accumulate() as PropheseeEvaluator.evaluate_buffer
+ * (utils/evaluation/prophesee/evaluator.py:73-110) drives them: frame f owns gt rows gt_ptr[f]..gt_ptr[f+1] and detection rows
+ * dt_ptr[f]..dt_ptr[f+1] (all device arrays): t int64 (us), xywh fp32 [n,4] top-left corner format, cls int32, score fp32
+ * (= class_confidence, coco_eval.py:176).  only_class >= 0 evaluates that class alone (evaluator.py:95-105), -1 all classes.
+ * iou_thrs / rec_thrs: HOST arrays of 10 / 101 doubles (np.linspace(.5,.95,10), np.linspace(0,1,101) of pycocotools Params).
+ * Outputs (device fp64): precision [10, 101, K, 4, 3] (-1 = undefined), recall [10, K, 4, 3] in COCOeval.eval's layout
+ * (IoU thr, recall thr, class, area range all/small/medium/large, maxDets 1/10/100); counts int32 [3] = images, detections kept,
+ * status (1: more than 128 gt boxes or 2048 detections of one class in a frame).  The summary numbers (AP, AP50, ...) are means
+ * over these arrays (COCOeval.summarize), taken by the caller. */
+int64_t leod_coco_eval_workspace_bytes(int F, int num_classes);
+int leod_coco_eval(const int64_t *gt_t, const float *gt_xywh, const int32_t *gt_cls, const int32_t *gt_ptr, const int64_t *dt_t,
+                   const float *dt_xywh, const int32_t *dt_cls, const float *dt_score, const int32_t *dt_ptr, int F, int num_classes,
+                   int64_t skip_ts, int min_box_diag, int min_box_side, int only_class, const double *iou_thrs, const double *rec_thrs,
+                   void *ws, double *precision, double *recall, int32_t *counts, void *stream);
+
 /* ------------------------------------------------------------------ event binning
  * Replaces data/utils/representations.py:78-123 (StackedHistogram.construct).
  * x,y,p: device int32 [n]; t: device int64 [n] (sorted); out: device uint8 [2*bins, H, W].

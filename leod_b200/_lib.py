@@ -111,6 +111,9 @@ def _declare(lib):
         'leod_upload_small': (I, [VP, VP, c_int64, VP]),
         'leod_augment_ev_repr': (I, [VP, VP, I, I, I, I, I, POINTER(AugmState), VP]),
         'leod_augment_labels': (I, [VP, VP, c_int64, I, POINTER(AugmState), VP, VP]),
+        'leod_coco_eval_workspace_bytes': (c_int64, [I, I]),
+        'leod_coco_eval': (I, [VP, VP, VP, VP, VP, VP, VP, VP, VP, I, I, c_int64, I, I, I, POINTER(ctypes.c_double), POINTER(ctypes.c_double),
+                               VP, VP, VP, VP, VP]),
         'leod_voxel_bin': (I, [VP, VP, VP, VP, c_int64, I, I, I, I, I, VP, VP]),
         'leod_adamw_ema': (I, [VP, VP, VP, VP, VP, c_int64, I, F, F, F, F, F, F, F, VP]),
     }
@@ -134,7 +137,7 @@ EXPORTED_SYMBOLS = ['leod_last_error', 'leod_abi_version', 'leod_launch_count', 
                     'leod_detect_buffer_count', 'leod_detect_counter_count', 'leod_detect_num_anchors', 'leod_detect_bind',
                     'leod_detect_prepare', 'leod_detect_reserve', 'leod_detect_set_allreduce', 'leod_fpn_head_fwd',
                     'leod_simota_loss_fwd', 'leod_simota_loss_bwd', 'leod_simota_assignment', 'leod_detect_get_raw', 'leod_detect_get_raw_grad', 'leod_detect_set_raw_grad', 'leod_fpn_head_bwd', 'leod_postprocess', 'leod_pred2label', 'leod_tta_merge', 'leod_track_workspace_bytes', 'leod_track_filter', 'leod_pack_bbox',
-                    'leod_upload_small', 'leod_augment_ev_repr', 'leod_augment_labels', 'leod_voxel_bin', 'leod_adamw_ema']
+                    'leod_upload_small', 'leod_augment_ev_repr', 'leod_augment_labels', 'leod_coco_eval_workspace_bytes', 'leod_coco_eval', 'leod_voxel_bin', 'leod_adamw_ema']
 
 
 def lib():

@@ -463,6 +463,58 @@ def gen_augment():
     print('augment_cases.npz')
 
 
+def gen_eval():
+    """The reference's own half of the evaluation (everything before pycocotools): filter_boxes (io/box_filtering.py:18-36) with the
+    thresholds of evaluation.py:24-33, _match_times and _to_coco_format (metrics/coco_eval.py:65-94, 140-194) on seeded per-frame
+    buffers built like to_prophesee builds them (io/box_loading.py:58-107).  pycocotools is absent here: COCOeval itself is not run."""
+    import importlib.util
+    import types
+    from utils.evaluation.prophesee.io.box_filtering import filter_boxes
+    from data.genx_utils.labels import BBOX_DTYPE
+    for name in ('pycocotools', 'pycocotools.coco', 'pycocotools.cocoeval'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules['pycocotools.coco'].COCO = None
+    sys.modules['pycocotools.cocoeval'].COCOeval = None
+    torch.cuda.get_device_name = lambda *a, **k: 'cpu'          # metrics/coco_eval.py:17 queries it at import time
+    spec = importlib.util.spec_from_file_location('ref_coco_eval', os.path.join(refimport.REF, 'utils/evaluation/prophesee/metrics/coco_eval.py'))
+    ce = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ce)
+    sys.path[:0] = [os.path.join(HERE, '..'), os.path.join(HERE, '..', '..')]
+    from helpers import EVAL_CASES, eval_inputs
+    out = {}
+    for ci, (camera, ds2, F, seed) in enumerate(EVAL_CASES):
+        gts, dts = eval_inputs(camera, ds2, F, seed)
+
+        def rec(d, with_score):
+            r = np.zeros(len(d['cls']), dtype=BBOX_DTYPE)
+            r['t'], r['x'], r['y'], r['w'], r['h'] = d['t'], d['xywh'][:, 0], d['xywh'][:, 1], d['xywh'][:, 2], d['xywh'][:, 3]
+            r['class_id'] = d['cls']
+            r['class_confidence'] = d['score'] if with_score else 1.0
+            return r
+        diag, side = (60, 20) if camera == 'gen4' else (30, 10)          # evaluation.py:24-33
+        if ds2:
+            diag, side = diag // 2, side // 2
+        fl = lambda x: filter_boxes(x, int(5e5), diag, side)  # noqa: E731
+        flat_gt, flat_dt, frames = [], [], []
+        for f, (g, d) in enumerate(zip(gts, dts)):                          # coco_eval.py:47-60
+            g, d = fl(rec(g, False)), fl(rec(d, True))
+            all_ts = np.unique(g['t'])
+            gw, dw = ce._match_times(all_ts, g, d, 50000)
+            flat_gt += gw
+            flat_dt += dw
+            frames += [f] * len(gw)
+        cats = [{'id': i + 1, 'name': str(i), 'supercategory': 'none'} for i in range(3 if camera == 'gen4' else 2)]
+        dataset, results = ce._to_coco_format(flat_gt, flat_dt, cats)
+        out[f'{ci}/frames'] = np.array(frames, np.int64)
+        out[f'{ci}/ann'] = np.array([[a['image_id'], a['category_id'], *a['bbox'], a['area']] for a in dataset['annotations']],
+                                    np.float64).reshape(-1, 7)
+        out[f'{ci}/res'] = np.array([[r['image_id'], r['category_id'], *r['bbox'], r['score']] for r in results], np.float64).reshape(-1, 7)
+        print(ci, camera, ds2, 'images', len(frames), 'of', F, 'ann', len(dataset['annotations']), 'res', len(results))
+    out['n'] = np.int64(len(EVAL_CASES))
+    np.savez_compressed(os.path.join(HERE, 'eval_cases.npz'), **out)
+    print('eval_cases.npz')
+
+
 if __name__ == '__main__':
     torch.set_num_threads(4)
     gen_net()
@@ -473,3 +525,4 @@ if __name__ == '__main__':
     gen_tracking()
     gen_fullsize()
     gen_augment()
+    gen_eval()

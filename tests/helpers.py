@@ -100,3 +100,47 @@ def augment_inputs(H, W, L, C, seed):
         rows = np.stack((np.full(n, 1000.0 + t), x, y, w, h, rng.integers(0, 2, n).astype(np.float64), np.ones(n), np.ones(n)), 1)
         labels.append(rows.astype(np.float32))
     return ev, labels
+
+
+# ---- evaluation cases (tests/golden/eval_cases.npz): (camera, downsampled_by_2, frames, seed)
+EVAL_CASES = [('gen1', False, 24, 1), ('gen4', True, 30, 2), ('gen4', False, 12, 3)]
+
+
+def eval_inputs(camera, ds2, n_frames, seed, max_gt=8, det_noise=6.0, fp_rate=3.0, miss_p=0.15):
+    """Per-frame ground truth and detections as the evaluator buffers hold them: dict(t int64, xywh fp32 [n,4], cls int64, score fp32).
+    Detections = jittered copies of most gt boxes + false positives; some boxes violate the Prophesee size / time filters, some frames
+    lose all their gt to the filter, some have no detection."""
+    rng = np.random.default_rng(7000 + seed)
+    H, W = ((360, 640) if ds2 else (720, 1280)) if camera == 'gen4' else (240, 304)
+    K = 3 if camera == 'gen4' else 2
+    gts, dts = [], []
+    for f in range(n_frames):
+        t = np.int64(100000 * (f + 1) + (f % 3) * 150000)          # the first frames lie before 0.5 s
+        n = int(rng.integers(0 if f % 7 == 3 else 1, max_gt + 1))
+        w = rng.uniform(4, W * 0.4, n).astype(np.float32)
+        h = rng.uniform(4, H * 0.4, n).astype(np.float32)
+        if f % 5 == 4:
+            w[:], h[:] = 6, 6                                       # every gt box too small: the frame is no image
+        x = rng.uniform(0, W - w).astype(np.float32)
+        y = rng.uniform(0, H - h).astype(np.float32)
+        cls = rng.integers(0, K, n)
+        gts.append(dict(t=np.full(n, t), xywh=np.stack((x, y, w, h), 1).reshape(-1, 4).astype(np.float32), cls=cls.astype(np.int64)))
+        keep = rng.random(n) > miss_p
+        jit = rng.normal(0, det_noise, (int(keep.sum()), 4)).astype(np.float32)
+        dx = gts[-1]['xywh'][keep] + jit
+        dx[:, 2:] = np.maximum(dx[:, 2:], 2)
+        dc = cls[keep].copy()
+        flip = rng.random(len(dc)) < 0.1
+        dc[flip] = (dc[flip] + 1) % K
+        nf = int(rng.poisson(fp_rate)) if f % 6 != 5 else 0
+        fw = rng.uniform(4, W * 0.3, nf).astype(np.float32)
+        fh = rng.uniform(4, H * 0.3, nf).astype(np.float32)
+        fx = np.stack((rng.uniform(0, W - fw), rng.uniform(0, H - fh), fw, fh), 1).astype(np.float32).reshape(-1, 4)
+        xywh = np.concatenate((dx.reshape(-1, 4), fx), 0).astype(np.float32)
+        c = np.concatenate((dc, rng.integers(0, K, nf))).astype(np.int64)
+        score = np.round(rng.uniform(0.05, 1.0, len(c)), 2).astype(np.float32)      # rounded: ties between detections occur
+        if f % 6 == 5:
+            xywh, c, score = xywh[:0], c[:0], score[:0]
+        p = rng.permutation(len(c))
+        dts.append(dict(t=np.full(len(c), t), xywh=xywh[p], cls=c[p], score=score[p]))
+    return gts, dts

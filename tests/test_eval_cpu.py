@@ -1,0 +1,72 @@
+"""Evaluation oracle.  The Prophesee half (box filter, frame -> image windows, COCO records) is pinned against
+fixtures produced by the reference's own filter_boxes / _match_times / _to_coco_format (tests/golden/make_golden.py::gen_eval).
+pycocotools (third party, not vendored, absent here) cannot be run: its restatement is checked on cases with known answers."""
+import os
+
+import numpy as np
+
+from helpers import EVAL_CASES, eval_inputs
+from oracle import coco_eval as oc
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'eval_cases.npz'))
+
+
+def test_prophesee_half_matches_reference_functions():
+    assert int(GOLD['n']) == len(EVAL_CASES)
+    for ci, (camera, ds2, F, seed) in enumerate(EVAL_CASES):
+        gts, dts = eval_inputs(camera, ds2, F, seed)
+        frames, ann, res = oc.to_coco_records(gts, dts, camera, ds2)
+        np.testing.assert_array_equal(frames, GOLD[f'{ci}/frames'])
+        np.testing.assert_array_equal(ann, GOLD[f'{ci}/ann'])        # image id, category id, box, area (fp32 product)
+        np.testing.assert_array_equal(res, GOLD[f'{ci}/res'])
+
+
+def _frame(boxes, cls, score=None, t=10 ** 6):
+    d = dict(t=np.full(len(cls), t, np.int64), xywh=np.asarray(boxes, np.float32).reshape(-1, 4), cls=np.asarray(cls, np.int64))
+    if score is not None:
+        d['score'] = np.asarray(score, np.float32)
+    return d
+
+
+def test_perfect_detections_score_one():
+    gts, dts = eval_inputs('gen1', False, 16, 5, det_noise=0.0, fp_rate=0.0, miss_p=0.0)
+    for g, d in zip(gts, dts):          # detections = the ground truth itself
+        d['xywh'], d['cls'], d['score'], d['t'] = g['xywh'].copy(), g['cls'].copy(), np.full(len(g['cls']), 0.9, np.float32), g['t'].copy()
+    stats, precision, recall = oc.evaluate_frames(gts, dts, 'gen1', False)
+    assert all(abs(stats[i] - 1.0) < 1e-12 for i in (0, 1, 2, 8))
+    p100 = precision[..., 0, 2]                      # all areas, maxDets 100: 1 / (1 + eps) everywhere
+    assert ((p100 == -1.0) | (abs(p100 - 1.0) < 1e-12)).all() and (p100 > 0).any()
+
+
+def test_worked_example_ap50():
+    """One image, one class, two gt boxes; detections by descending score: TP, FP, TP.  Precision/recall points (1, .5), (.5, .5),
+    (2/3, 1); envelope (1, 2/3, 2/3); 51 recall thresholds <= 0.5 read 1, the other 50 read 2/3."""
+    g = _frame([[10, 10, 40, 40], [100, 100, 50, 50]], [0, 0])
+    d = _frame([[10, 10, 40, 40], [200, 20, 40, 40], [100, 100, 50, 50]], [0, 0, 0], [0.9, 0.8, 0.7])
+    stats, precision, recall = oc.evaluate_frames([g], [d], 'gen1', False)
+    want = (51 * 1.0 + 50 * (2.0 / 3.0)) / 101
+    assert abs(precision[0, :, 0, 0, 2].mean() - want) < 1e-12
+    assert abs(stats[1] - want) < 1e-12 and abs(stats[0] - want) < 1e-12       # exact boxes: the same at every IoU threshold
+    assert recall[0, 0, 0, 2] == 1.0 and recall[0, 0, 0, 0] == 0.5              # maxDets = 1 sees only the first detection
+    assert (precision[:, :, 1] == -1).all()                                      # class without ground truth stays undefined
+
+
+def test_iou_threshold_and_area_ranges():
+    """A detection shifted so that IoU = 0.6 is a TP up to the 0.60 threshold only; a 25x25 gt is 'small', 50x50 'medium'."""
+    g = _frame([[0, 0, 50, 50], [200, 100, 25, 25]], [0, 0])
+    d = _frame([[12.5, 0, 50, 50], [200, 100, 25, 25]], [0, 0], [0.9, 0.8])     # IoU(first) = 37.5*50 / (2*2500 - 1875) = 0.6
+    stats, precision, recall = oc.evaluate_frames([g], [d], 'gen1', False)
+    assert abs(oc.bbox_iou([[12.5, 0, 50, 50]], [[0, 0, 50, 50]])[0, 0] - 0.6) < 1e-12
+    np.testing.assert_array_equal(recall[:, 0, 2, 2], [1, 1, 1] + [0] * 7)       # medium: matched at 0.50, 0.55, 0.60
+    np.testing.assert_array_equal(recall[:, 0, 1, 2], [1] * 10)                  # small: exact box
+    assert abs(stats[3] - 1.0) < 1e-12 and abs(stats[4] - 0.3) < 1e-12 and stats[5] == -1    # AP_S, AP_M, AP_L (no large gt)
+
+
+def test_filter_drops_frames_and_boxes():
+    g_early = _frame([[0, 0, 50, 50]], [0], t=400000)                            # before 0.5 s: no image
+    g_small = _frame([[0, 0, 8, 60]], [0])                                       # side < 10: no image
+    g_ok = _frame([[0, 0, 50, 50], [60, 60, 9, 9]], [0, 1])                      # second box filtered
+    d = _frame([[0, 0, 50, 50]], [0], [0.5])
+    frames, ann, res = oc.to_coco_records([g_early, g_small, g_ok], [dict(d, t=np.full(1, 400000)), d, d], 'gen1', False)
+    assert frames.tolist() == [2] and len(ann) == 1 and len(res) == 1
+    assert oc.evaluate_frames([g_early], [dict(d, t=np.full(1, 400000))], 'gen1', False) is None
