@@ -507,27 +507,10 @@ def run_train(args, wl, rank, local_rank, world):
     # streams before step i computes (double buffering, as a prefetching input pipeline does), and the loss of every step is
     # read back to the host.
     h2d = host[0][0].numel()
-    NCOPY = args.copy_streams     # the upload is split along L over several streams (one DMA engine does not fill the link)
-    copy_streams = [torch.cuda.Stream() for _ in range(NCOPY)]
-    dev_buf = [torch.empty_like(host[0][0], device=dev) for _ in range(2)]
-    copied = [[torch.cuda.Event() for _ in range(NCOPY)] for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    bounds = [L * c // NCOPY for c in range(NCOPY + 1)]
-
-    def issue_copy(i):
-        slot = i % 2
-        src = host[i % n_batches][0]
-        for c, cs in enumerate(copy_streams):
-            if bounds[c] == bounds[c + 1]:
-                continue
-            with torch.cuda.stream(cs):
-                cs.wait_event(consumed[slot])             # the step that last read this buffer has finished
-                dev_buf[slot][bounds[c]:bounds[c + 1]].copy_(src[bounds[c]:bounds[c + 1]], non_blocking=True)
-                copied[slot][c].record(cs)
-    for c in consumed:
-        c.record()
+    from leod_b200.data.feeder import PinnedBatchFeeder
+    feeder = PinnedBatchFeeder(host[0][0].shape, dev, n_buffers=2, n_streams=args.copy_streams)
     # labels, index lists and the first-sample mask are HOST tensors here; the step uploads them itself (leod_upload_small)
-    e2e_batches = [[make_batch(wl, dev_buf[s], host[j][1], host[j][2]) for j in range(n_batches)] for s in range(2)]
+    e2e_batches = [[make_batch(wl, feeder.buf[s], host[j][1], host[j][2]) for j in range(n_batches)] for s in range(2)]
     lag = max(0, args.e2e_lag)
     NLAG = lag + 1
     loss_pinned = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(NLAG)]
@@ -535,18 +518,15 @@ def run_train(args, wl, rank, local_rank, world):
     loss_host = None
     barrier()
     e0.record()
-    issue_copy(0)
+    feeder.submit(host[0][0])
     for i in range(args.steps):
         slot = i % 2
-        for c, ev_c in enumerate(copied[slot]):
-            if bounds[c] != bounds[c + 1]:
-                torch.cuda.current_stream().wait_event(ev_c)
+        ev_dev = feeder.acquire()                  # the compute stream waits for this batch's upload
+        assert ev_dev is feeder.buf[slot]
         loss = train_step(e2e_batches[slot][i % n_batches])
-        consumed[slot].record()
-        # the next batch's bulk upload is issued AFTER this step has been enqueued: the step's own small uploads (label and
-        # index tensors) would otherwise queue behind the bulk copy on the host->device engine and stall the stream
+        feeder.release()
         if i + 1 < args.steps:
-            issue_copy(i + 1)
+            feeder.submit(host[(i + 1) % n_batches][0])      # copies on the copy streams while step i computes
         # device -> host read of EVERY step's result, `lag` steps late (as an asynchronous logger does) so that the host keeps
         # enqueuing work while the step runs; the outstanding ones are read before the region closes
         loss_pinned[i % NLAG].copy_(loss.detach(), non_blocking=True)
@@ -584,7 +564,7 @@ def run_train(args, wl, rank, local_rank, world):
 
     ref_gpu, cpu = None, None
     if rank == 0 and world == 1 and not args.no_reference_gpu:
-        del dev_buf, e2e_batches
+        del feeder, e2e_batches
         torch.cuda.empty_cache()
         try:
             ref_gpu = time_reference_gpu(wl if not selftrain else dict(wl, label_t=tuple(range(L))), args.ref_precision, 5, 3, dev)
@@ -725,25 +705,15 @@ def run_sweep(args, rank, local_rank, world):
     e0.record()
     # end to end: every step's chunk comes from pinned host memory (uploaded on a copy stream while the previous chunk computes, as
     # a prefetching loader does) and every step's labels are read back on the host before the next step is enqueued
-    cs = torch.cuda.Stream()
-    dev_buf = [torch.empty_like(resident[0]) for _ in range(2)]
-    up_done = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
-
-    def issue_upload(i):
-        with torch.cuda.stream(cs):
-            cs.wait_event(free[i % 2])
-            dev_buf[i % 2].copy_(host[i % 3], non_blocking=True)
-            up_done[i % 2].record(cs)
-    for f in free:
-        f.record()
-    issue_upload(0)
+    from leod_b200.data.feeder import PinnedBatchFeeder
+    feeder = PinnedBatchFeeder(host[0].shape, dev, n_buffers=2, n_streams=4)
+    feeder.submit(host[0])
     for i in range(args.steps):
+        ev_dev = feeder.acquire()
         if i + 1 < args.steps:
-            issue_upload(i + 1)
-        torch.cuda.current_stream().wait_event(up_done[i % 2])
-        out = pl.predict_step(batch_of(dev_buf[i % 2], False))
-        free[i % 2].record()
+            feeder.submit(host[(i + 1) % 3])
+        out = pl.predict_step(batch_of(ev_dev, False))
+        feeder.release()
         n_boxes = sum(len(l) for row in out[0] for l in row if l is not None)    # labels read back on the host
     e1.record()
     barrier()

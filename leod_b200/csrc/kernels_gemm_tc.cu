@@ -492,6 +492,7 @@ int pick_bn(int M, int N, int K) {
 //   1024 B apart (SBO), successive 64-element MN blocks one box (8192 B) apart (LBO).
 struct TnArgs {
   float *dW; int ldw;
+  float *dbias;       // != NULL: dbias[n] += sum_m dY[m,n], computed by the k-tile-0 CTAs as one more MMA against a tile of ones
   int M, N, K;
   int BKt;            // output columns per CTA (multiple of 64, <= 256)
   int rows_per_split; // multiple of 64
@@ -507,7 +508,10 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
                                                                  const __grid_constant__ CUtensorMap mapX, const TnArgs a) {
   pdl_launch_dependents();   // the next kernel of the stream may start its own prologue
   extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *smem_al = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *ones = smem_al;                                 // one operand box of bf16 1.0 (bias gradient), then the ring
+  uint8_t *smem = smem_al + TN_BOX_BYTES;
+  const bool do_bias = a.dbias != nullptr && blockIdx.y == 0;
   const int nbx = a.BKt / 64;                              // X boxes per stage
   const int stage_bytes = (2 + nbx) * TN_BOX_BYTES;
   uint64_t *bars = (uint64_t *)(smem + (size_t)a.stages * stage_bytes);
@@ -534,6 +538,11 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (do_bias) {   // every element is 1.0, so the swizzled operand layout needs no care
+    for (int i = threadIdx.x; i < TN_BOX_BYTES / 16; i += blockDim.x)
+      reinterpret_cast<uint4 *>(ones)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -559,7 +568,8 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(TILE_M, a.BKt, 1, 1);
+      const uint32_t idesc = make_idesc(TILE_M, a.BKt, 1, 1), idesc_ones = make_idesc(TILE_M, 64, 1, 1);
+      const uint64_t odesc = make_desc(smem_u32(ones), TN_BOX_BYTES, 1024);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % a.stages;
         const uint32_t ph = (kb / a.stages) & 1;
@@ -572,6 +582,10 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
           // 16 tokens per MMA = 16 rows of 128 B = 2048 B (>>4: +128)
           tc_mma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (kb | k) != 0);
         }
+        if (do_bias) {   // column sums of the dY tile: the same A operand against ones, accumulated right of the dW tile
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem_base + (uint32_t)a.BKt, adesc + 128 * k, odesc + 128 * k, idesc_ones, (kb | k) != 0);
+        }
         tc_commit(smem_u32(&empty_bar[s]));
       }
       tc_commit(smem_u32(tmem_full));
@@ -581,6 +595,11 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
     const int n = n0 + quarter * 32 + lane;
     mbar_wait(smem_u32(tmem_full), 0);
     tc_fence_after();
+    if (do_bias) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a.BKt, r);
+      if (n < a.N) atomicAdd(a.dbias + n, __uint_as_float(r[0]));
+    }
     for (int c = 0; c < a.BKt; c += 16) {
       uint32_t r[16];
       tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, r);
@@ -614,58 +633,6 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tn_tc_kernel(const __grid_co
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
   }
-}
-
-// column sums of a bf16 matrix into fp32 (bias gradients).  Every thread owns one 8-column chunk (one 16-byte load per
-// row) and walks down the rows with a stride chosen so that a warp reads consecutive chunks: fully coalesced, 4 loads
-// in flight per thread.  blockDim.x is a multiple of the chunks per row, so the chunk of a thread never changes.
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const bf16 *__restrict__ Y, int ldy, float *__restrict__ out, int M, int N) {
-  pdl_prologue();
-  __shared__ float red[256][9];
-  const int nc = N >> 3;
-  const int tid = threadIdx.x;
-  const int chunk = tid % nc;
-  const int rows_per_pass = blockDim.x / nc;
-  const int64_t row_stride = (int64_t)gridDim.x * rows_per_pass;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const bf16 *base = Y + (size_t)chunk * 8;
-  int64_t m = (int64_t)blockIdx.x * rows_per_pass + tid / nc;
-  for (; m + 3 * row_stride < M; m += 4 * row_stride) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4 *>(base + (size_t)(m + u * row_stride) * ldy);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bf16 *e = reinterpret_cast<const bf16 *>(&v[u]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(e[j]);
-    }
-  }
-  for (; m < M; m += row_stride) {
-    const uint4 v = *reinterpret_cast<const uint4 *>(base + (size_t)m * ldy);
-    const bf16 *e = reinterpret_cast<const bf16 *>(&v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += __bfloat162float(e[j]);
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) red[tid][j] = acc[j];
-  __syncthreads();
-  for (int i = tid; i < nc * 8; i += blockDim.x) {
-    const int c = i >> 3, j = i & 7;
-    float t = 0.f;
-    for (int r = 0; r < rows_per_pass; ++r) t += red[r * nc + c][j];
-    atomicAdd(&out[c * 8 + j], t);
-  }
-}
-// generic fallback (N not a multiple of 8 or more than 256 chunks per row)
-__global__ void colsum_bf16_slow_kernel(const bf16 *__restrict__ Y, int ldy, float *__restrict__ out, int M, int N, int rows_per_block) {
-  pdl_prologue();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
-  float acc = 0.f;
-  for (int m = m0; m < m1; ++m) acc += __bfloat162float(Y[(size_t)m * ldy + n]);
-  atomicAdd(&out[n], acc);
 }
 
 // ============================================================================================ fused ConvLSTM recurrence
@@ -1462,6 +1429,7 @@ int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int l
   if (taps) a.taps = *taps;
   const int ntap = a.taps.n > 1 ? a.taps.n : 1;
   a.dW = dW; a.ldw = ldw; a.M = M; a.N = N; a.K = K;
+  a.dbias = dbias;
   a.BKt = K >= 256 ? 256 : (int)round_up(K, 64);
   const int tn = ceil_div(N, TILE_M), tk = ceil_div(K, a.BKt);
   // each split ends in an atomic epilogue over the whole output tile, so splits are only worth it when
@@ -1480,33 +1448,19 @@ int gemm_tn_tc(const void *dY, int ldy, const void *X, int ldx, float *dW, int l
   const int nkb = a.rows_per_split / 64;
   a.stages = nkb < 4 ? nkb : 4;
   a.tmem_cols = 32;
-  while (a.tmem_cols < a.BKt) a.tmem_cols *= 2;
+  while (a.tmem_cols < a.BKt + (dbias ? 64 : 0)) a.tmem_cols *= 2;
   CUtensorMap mY, mX;
   LEOD_TRY(make_map(&mY, dY, N, M, ldy, 64, 64));
   LEOD_TRY(make_map(&mX, X, K, M, ldx, 64, 64));
   const int stage_bytes = (2 + a.BKt / 64) * TN_BOX_BYTES;
-  const size_t smem = (size_t)a.stages * stage_bytes + 1024 + (2 * a.stages + 2) * 8;
+  const size_t smem = (size_t)a.stages * stage_bytes + TN_BOX_BYTES + 1024 + (2 * a.stages + 2) * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    LEOD_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    LEOD_CUDA(cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(210 * 1024)));
     attr_set = true;
   }
   dim3 grid(tn, tk * ntap, splits);
   LEOD_LAUNCH((gemm_tn_tc_kernel), grid, NUM_THREADS, smem, st, mY, mX, a);
   LEOD_LAUNCH_CHECK();
-  if (dbias) {
-    const int nc = N / 8;
-    if (N % 8 == 0 && nc <= 256) {
-      const int threads = 256 / nc * nc, rows_per_pass = threads / nc;
-      int blocks = ceil_div(M, rows_per_pass * 4);
-      if (blocks > 148 * 8) blocks = 148 * 8;
-      LEOD_LAUNCH((colsum_bf16_kernel), blocks, threads, 0, st, (const bf16 *)dY, ldy, dbias, M, N);
-    } else {
-      const int rpb = (int)round_up(ceil_div(M, 148 * 2), 32);
-      dim3 g2(ceil_div(N, 128), ceil_div(M, rpb));
-      LEOD_LAUNCH((colsum_bf16_slow_kernel), g2, 128, 0, st, (const bf16 *)dY, ldy, dbias, M, N, rpb);
-    }
-    LEOD_LAUNCH_CHECK();
-  }
   return 0;
 }

@@ -101,3 +101,23 @@ def test_upload_small_roundtrip():
     assert all(torch.equal(d.cpu(), t) for d, t in zip(dev, many))
     with pytest.raises(RuntimeError):
         _lib.check(_lib.lib().leod_upload_small(_lib.ptr(dev[0]), many[0].data_ptr(), 256, None), 'pageable source')
+
+
+def test_pinned_batch_feeder_double_buffering():
+    from leod_b200.data.feeder import PinnedBatchFeeder
+    g = torch.Generator().manual_seed(1)
+    shape = (5, 2, 4, 48, 64)
+    host = [torch.randint(0, 255, shape, generator=g).to(torch.uint8).pin_memory() for _ in range(5)]
+    f = PinnedBatchFeeder(shape, 'cuda', n_buffers=2, n_streams=3)
+    f.submit(host[0])
+    sums = []
+    for i in range(5):
+        ev = f.acquire()
+        if i + 1 < 5:
+            f.submit(host[i + 1])                # overlaps the "step" below
+        sums.append(ev.long().sum())             # the step: reads the buffer on the current stream
+        assert torch.equal(ev.cpu(), host[i])
+        f.release()
+    assert [int(s) for s in sums] == [int(h.long().sum()) for h in host]
+    with pytest.raises(RuntimeError):
+        f.submit(torch.zeros(shape, dtype=torch.uint8))      # pageable memory is refused
