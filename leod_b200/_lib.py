@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_float, c_int, c_int32,
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libleod_b200.so')
+LIB_PATH = os.environ.get('LEOD_B200_LIB') or os.path.join(_HERE, 'lib', 'libleod_b200.so')      # the override serves kernel-variant experiments
 
 LEOD_F32, LEOD_BF16, LEOD_U8 = 0, 1, 2
 EPI_NONE, EPI_GELU, EPI_RESID, EPI_GELU_BWD = 0, 1, 2, 3

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(PP_THREADS) postprocess_kernel(const float *__
   float *c_score = sm;                          // [A]
   int *c_anchor = (int *)(c_score + A);         // [A]
   int *s_anchor = c_anchor + A;                 // [A]
-  float *s_box = (float *)(s_anchor + A);       // [4A]
+  float *s_box = (float *)(s_anchor + A);       // [4][A] (x1 | y1 | x2 | y2 planes: conflict-free in the NMS loop)
   unsigned char *s_sup = (unsigned char *)(s_box + 4 * (size_t)A);  // [A]
   __shared__ int n_cand, n_keep;
   __shared__ float red[PP_THREADS / 32];
@@ -74,10 +74,10 @@ __global__ void __launch_bounds__(PP_THREADS) postprocess_kernel(const float *__
     const float off = __fmul_rn((float)cls, off_unit);
     const float hw = __fmul_rn(r[2], 0.5f), hh = __fmul_rn(r[3], 0.5f);
     s_anchor[rank] = ai;
-    s_box[4 * rank + 0] = __fadd_rn(__fsub_rn(r[0], hw), off);
-    s_box[4 * rank + 1] = __fadd_rn(__fsub_rn(r[1], hh), off);
-    s_box[4 * rank + 2] = __fadd_rn(__fadd_rn(r[0], hw), off);
-    s_box[4 * rank + 3] = __fadd_rn(__fadd_rn(r[1], hh), off);
+    s_box[rank] = __fadd_rn(__fsub_rn(r[0], hw), off);
+    s_box[A + rank] = __fadd_rn(__fsub_rn(r[1], hh), off);
+    s_box[2 * A + rank] = __fadd_rn(__fadd_rn(r[0], hw), off);
+    s_box[3 * A + rank] = __fadd_rn(__fadd_rn(r[1], hh), off);
     s_sup[rank] = 0;
   }
   __syncthreads();
@@ -88,11 +88,11 @@ __global__ void __launch_bounds__(PP_THREADS) postprocess_kernel(const float *__
     if (s_sup[i]) continue;  // uniform: flags only change before a barrier
     const int kslot = n_keep;
     if (kslot >= max_det) break;
-    const float ix1 = s_box[4 * i], iy1 = s_box[4 * i + 1], ix2 = s_box[4 * i + 2], iy2 = s_box[4 * i + 3];
+    const float ix1 = s_box[i], iy1 = s_box[A + i], ix2 = s_box[2 * A + i], iy2 = s_box[3 * A + i];
     const float iarea = __fmul_rn(__fsub_rn(ix2, ix1), __fsub_rn(iy2, iy1));
     for (int j = i + 1 + tid; j < n; j += PP_THREADS) {
       if (s_sup[j]) continue;
-      const float jx1 = s_box[4 * j], jy1 = s_box[4 * j + 1], jx2 = s_box[4 * j + 2], jy2 = s_box[4 * j + 3];
+      const float jx1 = s_box[j], jy1 = s_box[A + j], jx2 = s_box[2 * A + j], jy2 = s_box[3 * A + j];
       const float w = fmaxf(__fsub_rn(fminf(ix2, jx2), fmaxf(ix1, jx1)), 0.f);
       const float h = fmaxf(__fsub_rn(fminf(iy2, jy2), fmaxf(iy1, jy1)), 0.f);
       const float inter = __fmul_rn(w, h);
@@ -100,21 +100,25 @@ __global__ void __launch_bounds__(PP_THREADS) postprocess_kernel(const float *__
       const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, jarea), inter));
       if (iou > nms_thre) s_sup[j] = 1;
     }
-    if (tid == 0) {
-      const float *r = p + (size_t)s_anchor[i] * stride;
-      int cls = 0;
-      float best = r[5];
-      for (int c = 1; c < ncls; ++c)
-        if (r[5 + c] > best) { best = r[5 + c]; cls = c; }
-      const float hw = __fmul_rn(r[2], 0.5f), hh = __fmul_rn(r[3], 0.5f);
-      float *d = o + (size_t)kslot * 7;
-      d[0] = __fsub_rn(r[0], hw); d[1] = __fsub_rn(r[1], hh); d[2] = __fadd_rn(r[0], hw); d[3] = __fadd_rn(r[1], hh);
-      d[4] = r[4]; d[5] = best; d[6] = (float)cls;
+    if (tid == 0) {      // the output rows are written after the loop: no global-memory latency inside the serial chain
+      c_anchor[kslot] = i;
       n_keep = kslot + 1;
     }
     __syncthreads();
   }
   __syncthreads();
+  const int nk = n_keep;
+  for (int k = tid; k < nk; k += PP_THREADS) {
+    const float *r = p + (size_t)s_anchor[c_anchor[k]] * stride;
+    int cls = 0;
+    float best = r[5];
+    for (int c = 1; c < ncls; ++c)
+      if (r[5 + c] > best) { best = r[5 + c]; cls = c; }
+    const float hw = __fmul_rn(r[2], 0.5f), hh = __fmul_rn(r[3], 0.5f);
+    float *d = o + (size_t)k * 7;
+    d[0] = __fsub_rn(r[0], hw); d[1] = __fsub_rn(r[1], hh); d[2] = __fadd_rn(r[0], hw); d[3] = __fadd_rn(r[1], hh);
+    d[4] = r[4]; d[5] = best; d[6] = (float)cls;
+  }
   if (tid == 0) count[b] = n_keep;
 }
 
@@ -250,16 +254,20 @@ __global__ void __launch_bounds__(TM_THREADS) tta_merge_kernel(const float *__re
       if (iou > nms_thre) s_sup[j] = 1;
     }
     if (tid == 0) {
-      const float *q = L + s_row[i] * 8;
-      float *d = O + (size_t)kslot * 8;
-      const float x2 = __fadd_rn(q[1], q[3]), y2 = __fadd_rn(q[2], q[4]);
-      d[0] = q[0]; d[1] = q[1]; d[2] = q[2]; d[3] = __fsub_rn(x2, q[1]); d[4] = __fsub_rn(y2, q[2]);
-      d[5] = q[5]; d[6] = q[6]; d[7] = q[7];
+      c_row[kslot] = i;
       n_keep = kslot + 1;
     }
     __syncthreads();
   }
   __syncthreads();
+  const int nk = n_keep;
+  for (int k = tid; k < nk; k += TM_THREADS) {
+    const float *q = L + s_row[c_row[k]] * 8;
+    float *d = O + (size_t)k * 8;
+    const float x2 = __fadd_rn(q[1], q[3]), y2 = __fadd_rn(q[2], q[4]);
+    d[0] = q[0]; d[1] = q[1]; d[2] = q[2]; d[3] = __fsub_rn(x2, q[1]); d[4] = __fsub_rn(y2, q[2]);
+    d[5] = q[5]; d[6] = q[6]; d[7] = q[7];
+  }
   if (tid == 0) out_count[f] = n_keep;
 }
 

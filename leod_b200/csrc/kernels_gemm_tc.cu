@@ -34,11 +34,18 @@ struct NtArgs {
   int tmem_cols;  // power of two >= 2 * acc_cols
   int staged;     // epilogue writes through shared memory (N multiple of 16: every chunk is full)
   int kpb;        // implicit-GEMM taps (g.taps.n > 1): k-blocks per tap
+  int bias_smem;  // the bias vector (N floats) is staged in shared memory once per CTA (staged epilogue, N <= 2048)
 };
 
 // epilogue warps: a multiple of 4 (one TMEM lane quarter each); the column range of a tile is split between the warps that
 // share a quarter.  The GELU epilogues are instruction-bound (erf + two outputs), so they get more warps.
-template <int EPI> struct NtEpiWarps { static constexpr int value = EPI == EPI_GELU ? 12 : 8; };
+#ifndef NT_EPI_WARPS
+#define NT_EPI_WARPS 8
+#endif
+#ifndef NT_EPI_WARPS_GELU
+#define NT_EPI_WARPS_GELU 12
+#endif
+template <int EPI> struct NtEpiWarps { static constexpr int value = EPI == EPI_GELU ? NT_EPI_WARPS_GELU : NT_EPI_WARPS; };
 template <int EPI> struct NtStageBytes { static constexpr int value = EPI == EPI_GELU ? 8192 : 4096; };   // per epilogue warp
 
 
@@ -132,15 +139,71 @@ __device__ __forceinline__ void gelu_parts_fast(float x, float &cdf, float &e) {
   const float h = 0.5f * p * e;               // 0.5 * (1 - erf(|x|/sqrt2))
   cdf = x >= 0.f ? 1.0f - h : h;
 }
+// Packed fp32 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two lanes per instruction).  The GELU epilogue is bound by instruction
+// issue, not by HBM (profiles/r02_ncu_full_gemm_nt_gelu_stage1_details.txt: 30 instructions per element, IPC 2.1 of 4), so the
+// polynomial part is evaluated on pairs of columns.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mov.b64 rc, {%6,%7};\n fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rd;\n mov.b64 ra, {%2,%3};\n mov.b64 rb, {%4,%5};\n add.rn.f32x2 rd, ra, rb;\n mov.b64 {%0,%1}, rd;}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// GELU(x) = x Phi(x) and GELU'(x) = Phi(x) + x phi(x) of two columns.  Same erf approximation as gelu_parts_fast (Abramowitz-Stegun
+// 7.1.26 on MUFU rcp / ex2), rearranged so that every multiply-add is packed:  E = phi(x) = 2^(-x^2 log2(e)/2 + log2(1/sqrt(2 pi))),
+// h = 0.5 erfc(|x|/sqrt2) = (poly(t) t) E with the 0.5 sqrt(2 pi) folded into the coefficients,  Phi = 0.5 + sign(x) (0.5 - h).
+__device__ __forceinline__ void gelu_pair(float2 x, float2 &H, float2 &G) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  const float2 u = ffma2(ax, splat2(0.3275911f * 0.70710678118654752440f), splat2(1.0f));
+  float2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  constexpr float k = 0.5f / 0.39894228040143267794f;
+  float2 p = ffma2(t, splat2(1.061405429f * k), splat2(-1.453152027f * k));
+  p = ffma2(p, t, splat2(1.421413741f * k));
+  p = ffma2(p, t, splat2(-0.284496736f * k));
+  p = ffma2(p, t, splat2(0.254829592f * k));
+  p = fmul2(p, t);
+  const float2 ea = ffma2(fmul2(x, x), splat2(-0.72134752044448170368f), splat2(-1.32574806473615f));
+  float2 E;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.x) : "f"(ea.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(E.y) : "f"(ea.y));
+  const float2 h = fmul2(p, E);
+  float2 d = ffma2(h, splat2(-1.0f), splat2(0.5f));      // 0.5 - h >= 0 up to rounding
+  d.x = __uint_as_float((__float_as_uint(d.x) & 0x7fffffffu) | (__float_as_uint(x.x) & 0x80000000u));
+  d.y = __uint_as_float((__float_as_uint(d.y) & 0x7fffffffu) | (__float_as_uint(x.y) & 0x80000000u));
+  const float2 cdf = fadd2(d, splat2(0.5f));
+  H = fmul2(x, cdf);
+  G = ffma2(x, E, cdf);
+}
 // Same arithmetic for a full 16-column chunk, but the results stay in registers (packed bf16) so the caller can
 // stage them in shared memory and write whole 128-byte lines: o = output chunk, t = pre-GELU chunk (EPI_GELU only).
 template <int EPI>
 __device__ __forceinline__ void nt_epilogue_compute(const GemmNT &g, const uint32_t (&r)[16], int m, int n, bool row_ok,
-                                                    uint4 (&o)[2], uint4 (&t)[2]) {
+                                                    uint4 (&o)[2], uint4 (&t)[2], const float *s_bias, const uint4 (&pre)[2]) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
-  if (g.bias) {
+  if (s_bias) {   // staged once per CTA: a broadcast shared-memory read instead of a global load per row and chunk
+    const float4 *b4 = reinterpret_cast<const float4 *>(s_bias + n);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 b = b4[q];
+      v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+    }
+  } else if (g.bias) {
     const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + n);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -152,20 +215,16 @@ __device__ __forceinline__ void nt_epilogue_compute(const GemmNT &g, const uint3
     uint32_t *tw = reinterpret_cast<uint32_t *>(t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {   // gelu and gelu' share erf and exp: aux gets the derivative, the backward is a multiply
-      float c0, e0, c1, e1;
-      gelu_parts_fast(v[2 * j], c0, e0);
-      gelu_parts_fast(v[2 * j + 1], c1, e1);
-      const __nv_bfloat162 pr = __floats2bfloat162_rn(fmaf(v[2 * j] * 0.39894228040143267794f, e0, c0),
-                                                      fmaf(v[2 * j + 1] * 0.39894228040143267794f, e1, c1));
+      float2 H, G;
+      gelu_pair(make_float2(v[2 * j], v[2 * j + 1]), H, G);
+      const __nv_bfloat162 pr = __floats2bfloat162_rn(G.x, G.y);
       tw[j] = *reinterpret_cast<const uint32_t *>(&pr);
-      v[2 * j] *= c0;
-      v[2 * j + 1] *= c1;
+      v[2 * j] = H.x;
+      v[2 * j + 1] = H.y;
     }
   } else if (EPI == EPI_RESID) {
-    if (row_ok) {
-      const uint4 *rx = reinterpret_cast<const uint4 *>((const bf16 *)g.R + (size_t)m * g.ldr + n);
-      const uint4 r0 = rx[0], r1 = rx[1];
-      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    if (row_ok) {   // the residual row piece was prefetched by the caller (global latency off the per-chunk chain)
+      const uint32_t w[8] = {pre[0].x, pre[0].y, pre[0].z, pre[0].w, pre[1].x, pre[1].y, pre[1].z, pre[1].w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {   // bf16 -> fp32 is a 16-bit shift
         v[2 * j] += __uint_as_float(w[j] << 16);
@@ -174,9 +233,7 @@ __device__ __forceinline__ void nt_epilogue_compute(const GemmNT &g, const uint3
     }
   } else if (EPI == EPI_GELU_BWD) {
     if (row_ok) {
-      const uint4 *ax = reinterpret_cast<const uint4 *>((const bf16 *)g.aux + (size_t)m * g.ldaux + n);
-      const uint4 r0 = ax[0], r1 = ax[1];
-      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+      const uint32_t w[8] = {pre[0].x, pre[0].y, pre[0].z, pre[0].w, pre[1].x, pre[1].y, pre[1].z, pre[1].w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         v[2 * j] *= __uint_as_float(w[j] << 16);
@@ -324,12 +381,33 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
     const int nchunks = a.BN >> 4;
     const int c_begin = (nchunks * part) / CS, c_end = (nchunks * (part + 1)) / CS;
     const GemmNT &g = a.g;
+    const float *s_bias = nullptr;
+    if (EPI >= 0 && a.bias_smem) {
+      float *sb = reinterpret_cast<float *>(stage_base + NtEpiWarps<EPI>::value * NtStageBytes<EPI>::value);
+      for (int i = threadIdx.x - 64; i < g.N; i += 32 * NtEpiWarps<EPI>::value) sb[i] = __ldg(g.bias + i);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NtEpiWarps<EPI>::value) : "memory");   // epilogue warps only
+      s_bias = sb;
+    }
     int j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int m0 = (tile / a.tiles_n) * TILE_M, n0 = (tile % a.tiles_n) * a.BN;
       const int buf = j & 1;
       const int m = m0 + quarter * 32 + lane;
       const bool row_ok = m < g.M;
+      // residual / GELU' operand of the epilogue: loaded one chunk ahead (the first one before the accumulator is even ready),
+      // so that the HBM latency of these per-row reads is not part of every chunk's dependent chain
+      constexpr bool PRE = (EPI == EPI_RESID || EPI == EPI_GELU_BWD);
+      uint4 pre[2][2];
+      const bf16 *psrc = EPI == EPI_RESID ? (const bf16 *)g.R : (const bf16 *)g.aux;
+      const int pld = EPI == EPI_RESID ? g.ldr : g.ldaux;
+      auto prefetch = [&](int cc, uint4(&dst)[2]) {
+        if (PRE && row_ok) {
+          const uint4 *q = reinterpret_cast<const uint4 *>(psrc + (size_t)m * pld + n0 + cc * 16);
+          dst[0] = q[0];
+          dst[1] = q[1];
+        }
+      };
+      if (c_begin < c_end) prefetch(c_begin, pre[0]);
       mbar_wait(smem_u32(&tmem_full[buf]), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * a.acc_cols);
@@ -345,10 +423,16 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
           for (int hh = 0; hh < 2; ++hh) {
             const int cc = c + hh;
             if (cc >= c_end) break;
-            tmem_ld_wait(rbuf[hh]);
-            if (cc + 1 < c_end) tmem_ld16_async(trow + (uint32_t)((cc + 1) * 16), rbuf[hh ^ 1]);
+            // 14 warps are allocated as 16 (granularity of four): 128 registers per thread.  The GELU epilogue does not fit a
+            // second in-flight TMEM chunk in that budget (it spilled into the hot loop), so it loads chunk by chunk; the other
+            // eleven warps hide the tcgen05.ld latency
+            constexpr int RB = EPI == EPI_GELU ? 0 : 1;
+            tmem_ld_wait(rbuf[hh & RB]);
+            if (RB && cc + 1 < c_end) tmem_ld16_async(trow + (uint32_t)((cc + 1) * 16), rbuf[(hh ^ 1) & RB]);
+            if (cc + 1 < c_end) prefetch(cc + 1, pre[hh ^ 1]);
             uint4 o[2], t[2];
-            nt_epilogue_compute<EPI>(g, rbuf[hh], m, n0 + cc * 16, row_ok, o, t);
+            nt_epilogue_compute<EPI>(g, rbuf[hh & RB], m, n0 + cc * 16, row_ok, o, t, s_bias, pre[hh]);
+            if (!RB && cc + 1 < c_end) tmem_ld16_async(trow + (uint32_t)((cc + 1) * 16), rbuf[0]);
             const int slot = (cc - gs) * 2, sw = lane & 7;
             *reinterpret_cast<uint4 *>(stC + lane * 128 + (((slot) ^ sw) << 4)) = o[0];
             *reinterpret_cast<uint4 *>(stC + lane * 128 + (((slot + 1) ^ sw) << 4)) = o[1];
@@ -1292,8 +1376,9 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   const int total_kb = a.nkb * ceil_div(a.tiles_m * a.tiles_n, num_sms());
   a.staged = (g.N % 16 == 0 && (((uintptr_t)g.bias) & 15) == 0 && !g.out_f32) ? 1 : 0;
   const bool gelu_like = a.staged && g.epi == EPI_GELU;
-  const int epi_warps = gelu_like ? NtEpiWarps<EPI_GELU>::value : 8;
-  const int epi_bytes = epi_warps * ((a.staged && g.epi == EPI_GELU) ? 8192 : 4096) + 256;
+  const int epi_warps = gelu_like ? NtEpiWarps<EPI_GELU>::value : NtEpiWarps<EPI_NONE>::value;
+  a.bias_smem = (a.staged && g.bias && g.N <= 2048) ? 1 : 0;
+  const int epi_bytes = epi_warps * ((a.staged && g.epi == EPI_GELU) ? 8192 : 4096) + 256 + (a.bias_smem ? (int)round_up(g.N * 4, 16) : 0);
   a.stages = std::min(std::min(4, (int)((224 * 1024 - epi_bytes - 2048) / stage_bytes)), std::max(total_kb, 1));
   CUtensorMap mA, mA2, mB, mB2;
   LEOD_TRY(make_map(&mA, g.A, tapped ? g.taps.cin : K1, g.M, g.lda, TILE_K, TILE_M));
