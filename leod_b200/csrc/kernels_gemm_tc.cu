@@ -34,6 +34,7 @@ struct NtArgs {
   int tmem_cols;  // power of two >= 2 * acc_cols
   int staged;     // epilogue writes through shared memory (N multiple of 16: every chunk is full)
   int kpb;        // implicit-GEMM taps (g.taps.n > 1): k-blocks per tap
+  int nbuf;       // accumulator buffers in TMEM (2..4): narrow tiles let the MMA warp run further ahead of the epilogue
   int bias_smem;  // the bias vector (N floats) is staged in shared memory once per CTA (staged epilogue, N <= 2048)
 };
 
@@ -290,8 +291,8 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
   const int b_stage_bytes = a.BN * TILE_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint64_t *bars = (uint64_t *)(smem + (size_t)a.stages * stage_bytes);
-  uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages, *tmem_empty = tmem_full + 2;
-  uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 2);
+  uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages, *tmem_empty = tmem_full + 4;
+  uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 4);
   // per epilogue warp: two 4 KB staging blocks (32 rows x 64 columns bf16), 128-byte aligned
   uint8_t *stage_base = (uint8_t *)(((uintptr_t)(tmem_slot + 4) + 127) & ~(uintptr_t)127);
 
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 4; ++b) {
       mbar_init(smem_u32(&tmem_full[b]), 1);
       mbar_init(smem_u32(&tmem_empty[b]), NtEpiWarps<EPI>::value);
     }
@@ -353,8 +354,8 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
       const uint32_t idesc = make_idesc(TILE_M, a.BN, 0, 0);
       int it = 0, j = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
-        const int buf = j & 1;
-        mbar_wait(smem_u32(&tmem_empty[buf]), ((j >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        const int buf = j % a.nbuf;
+        mbar_wait(smem_u32(&tmem_empty[buf]), ((j / a.nbuf) & 1) ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)(buf * a.acc_cols);
         for (int kb = 0; kb < a.nkb; ++kb, ++it) {
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
     int j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int m0 = (tile / a.tiles_n) * TILE_M, n0 = (tile % a.tiles_n) * a.BN;
-      const int buf = j & 1;
+      const int buf = j % a.nbuf;
       const int m = m0 + quarter * 32 + lane;
       const bool row_ok = m < g.M;
       // residual / GELU' operand of the epilogue: loaded one chunk ahead (the first one before the accumulator is even ready),
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
         }
       };
       if (c_begin < c_end) prefetch(c_begin, pre[0]);
-      mbar_wait(smem_u32(&tmem_full[buf]), (j >> 1) & 1);
+      mbar_wait(smem_u32(&tmem_full[buf]), (j / a.nbuf) & 1);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * a.acc_cols);
       uint32_t rbuf[2][16];
@@ -1370,8 +1371,9 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   a.tiles_m = ceil_div(g.M, TILE_M);
   a.tiles_n = ceil_div(g.N, a.BN);
   a.acc_cols = (int)round_up(a.BN, 32);
+  a.nbuf = std::max(2, std::min(4, 512 / a.acc_cols));
   a.tmem_cols = 32;
-  while (a.tmem_cols < 2 * a.acc_cols) a.tmem_cols *= 2;
+  while (a.tmem_cols < a.nbuf * a.acc_cols) a.tmem_cols *= 2;
   const int stage_bytes = A_STAGE_BYTES + a.BN * TILE_K * 2;
   const int total_kb = a.nkb * ceil_div(a.tiles_m * a.tiles_n, num_sms());
   a.staged = (g.N % 16 == 0 && (((uintptr_t)g.bias) & 15) == 0 && !g.out_f32) ? 1 : 0;
@@ -1390,7 +1392,7 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
     mA2 = mA;
     mB2 = mB;
   }
-  const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + (2 * a.stages + 4) * 8 + 16 + epi_bytes;
+  const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + (2 * a.stages + 8) * 8 + 16 + epi_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     LEOD_CUDA(cudaFuncSetAttribute(gemm_nt_tc_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024)));

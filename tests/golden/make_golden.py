@@ -379,7 +379,7 @@ def gen_tracking():
     np.savez_compressed(os.path.join(HERE, 'tracking_cases.npz'), **out)
 
 
-def gen_fullsize():
+def gen_fullsize(only=None):
     """Full-size runs of the REFERENCE itself (BASELINE configs[0]: RVT-tiny, 10 input channels, 1 x 240 x 304, one
     frame; and the configs[1] model RVT-small at batch 1, two frames) with name-seeded weights (tests/helpers.py:
     det_state_value), so only the small outputs are stored: stage-4 feature, final cell state of stage 4, decoded
@@ -389,7 +389,12 @@ def gen_fullsize():
     sizes = {'tiny': (32, 32, 0.33), 'small': (48, 24, 0.33), 'base': (64, 32, 0.67)}
     dsets = {'gen1': ((8, 10), 2, (256, 320), (240, 304)), 'gen4': ((6, 10), 3, (384, 640), (360, 640))}
     out = {}
+    path = os.path.join(HERE, 'fullsize_cases.npz')
+    if only is not None and os.path.exists(path):      # add cases without touching the committed ones
+        out = dict(np.load(path))
     for tag, (size, dataset, inch, B, L) in FULLSIZE_CASES.items():
+        if only is not None and tag not in only:
+            continue
         embed, dh, depth = sizes[size]
         part, ncls, in_res, frame = dsets[dataset]
         ref = YoloXDetector(model_cfg(embed, dh, part, ncls, depth, inch))

@@ -60,6 +60,8 @@ def det_events(seed: int, shape, density=0.1, vmax=6) -> torch.Tensor:
 FULLSIZE_CASES = {   # tag -> (size, dataset, input_channels, B, L): BASELINE configs[0] (plumbing case) and the configs[1] model
     'tiny_gen1_c10': ('tiny', 'gen1', 10, 1, 1),
     'small_gen1': ('small', 'gen1', 20, 1, 2),
+    'base_gen4': ('base', 'gen4', 20, 1, 1),          # BASELINE configs[2] model: partition (6, 10), dim_head 32, 3 classes, 384x640
+    'small_gen1_l8': ('small', 'gen1', 20, 1, 8),      # eight recurrent steps
 }
 
 

@@ -121,7 +121,7 @@ def test_ema_and_adamw_match_reference():
         np.testing.assert_allclose(p.numpy(), z[f'adamw/p{s + 1}'], rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize('tag', ['tiny_gen1_c10', 'small_gen1'])
+@pytest.mark.parametrize('tag', ['tiny_gen1_c10', 'small_gen1', 'base_gen4', 'small_gen1_l8'])
 def test_full_size_oracle_matches_reference_run(tag):
     """BASELINE configs[0] (RVT-tiny, 10 input channels, 240x304, one frame) and the configs[1] model at batch 1: the
     oracle against outputs of the reference itself (tests/golden/make_golden.py: gen_fullsize, name-seeded weights)."""
