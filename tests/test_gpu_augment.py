@@ -121,3 +121,21 @@ def test_pinned_batch_feeder_double_buffering():
     assert [int(s) for s in sums] == [int(h.long().sum()) for h in host]
     with pytest.raises(RuntimeError):
         f.submit(torch.zeros(shape, dtype=torch.uint8))      # pageable memory is refused
+
+
+def test_rnn_states_reset_with_host_mask():
+    """modules/utils/detection.py:95-157: `reset(worker_id, indices_or_bool_tensor)` with the collate's HOST bool mask zeroes the
+    selected rows of every state tensor on the device (one leod_upload_small for all of them, no pageable cudaMemcpy)."""
+    from leod_b200.modules.utils.detection import RNNStates
+    st = RNNStates()
+    g = torch.Generator().manual_seed(3)
+    states = [(torch.randn(4, 6, 3, 5, generator=g).cuda(), torch.randn(4, 6, 3, 5, generator=g).cuda()) for _ in range(4)]
+    ref = [(h.clone(), c.clone()) for h, c in states]
+    st.save_states_and_detach(worker_id=0, states=states)
+    mask = torch.tensor([True, False, False, True])
+    st.reset(worker_id=0, indices_or_bool_tensor=mask)
+    got = st.get_states(worker_id=0)
+    for (h, c), (rh, rc) in zip(got, ref):
+        rh[mask] = 0
+        rc[mask] = 0
+        assert torch.equal(h.cpu(), rh.cpu()) and torch.equal(c.cpu(), rc.cpu())
