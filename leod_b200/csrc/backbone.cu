@@ -640,26 +640,39 @@ extern "C" int leod_backbone_prepare(leod_backbone_t *h, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int dt = h->cfg.dtype;
   const float *P = h->params;
+  // 57 tensors -> two launches (items travel in the kernel parameters, PREP_BATCH_MAX per launch)
+  PrepBatch pb;
+  int blocks = 0;
+  auto add = [&](const float *src, const float *scale, void *dst, int ldd, void *dstT, int lddT, int N, int K, int perm, int Cin, int ksz,
+                 float *bias_out) -> int {
+    if (pb.n == PREP_BATCH_MAX) {
+      LEOD_TRY(prep_batch_launch(dt, pb, blocks, st));
+      pb.n = 0;
+      blocks = 0;
+    }
+    return prep_batch_add(pb, blocks, src, scale, dst, ldd, dstT, lddT, N, K, perm, Cin, ksz, bias_out);
+  };
   for (int s = 0; s < 4; ++s) {
     const StageD &d = h->d[s];
     const int C = d.C, R = h->cfg.mlp_ratio;
     const StageP &p = h->p[s];
     StageW &w = h->w[s];
-    LEOD_TRY(prep_weight(dt, P + p.convw, nullptr, w.Wconv, d.Kp, w.WconvT, C, C, d.K, s == 0 ? 2 : 1, d.Cin, d.ksz, st));
-    // the stem has no input gradient, so its transposed copy is unused: it holds the FP16 copy the implicit-GEMM forward reads
-    if (s == 0 && dt == LEOD_BF16) LEOD_TRY(stem_weight_to_f16(w.Wconv, w.WconvT, (int64_t)C * d.Kp, st));
+    LEOD_TRY(add(P + p.convw, nullptr, w.Wconv, d.Kp, w.WconvT, C, C, d.K, s == 0 ? 2 : 1, d.Cin, d.ksz, nullptr));
     for (int b = 0; b < 2; ++b) {
       const BlockP &q = p.blk[b];
       BlockW &bw = w.blk[b];
-      LEOD_TRY(prep_weight(dt, P + q.qkvw, nullptr, bw.Wqkv, C, bw.WqkvT, 3 * C, 3 * C, C, 0, 0, 0, st));
-      LEOD_TRY(prep_weight(dt, P + q.projw, P + q.ls1, bw.Wproj, C, bw.WprojT, C, C, C, 0, 0, 0, st));
-      LEOD_TRY(prep_scaled_bias(P + q.projb, P + q.ls1, bw.bproj, C, st));
-      LEOD_TRY(prep_weight(dt, P + q.fc1w, nullptr, bw.W1, C, bw.W1T, R * C, R * C, C, 0, 0, 0, st));
-      LEOD_TRY(prep_weight(dt, P + q.fc2w, P + q.ls2, bw.W2, R * C, bw.W2T, C, C, R * C, 0, 0, 0, st));
-      LEOD_TRY(prep_scaled_bias(P + q.fc2b, P + q.ls2, bw.b2, C, st));
+      LEOD_TRY(add(P + q.qkvw, nullptr, bw.Wqkv, C, bw.WqkvT, 3 * C, 3 * C, C, 0, 0, 0, nullptr));
+      LEOD_TRY(add(P + q.projw, P + q.ls1, bw.Wproj, C, bw.WprojT, C, C, C, 0, 0, 0, nullptr));
+      LEOD_TRY(add(P + q.projb, P + q.ls1, nullptr, 0, nullptr, 0, C, 1, 0, 0, 0, bw.bproj));
+      LEOD_TRY(add(P + q.fc1w, nullptr, bw.W1, C, bw.W1T, R * C, R * C, C, 0, 0, 0, nullptr));
+      LEOD_TRY(add(P + q.fc2w, P + q.ls2, bw.W2, R * C, bw.W2T, C, C, R * C, 0, 0, 0, nullptr));
+      LEOD_TRY(add(P + q.fc2b, P + q.ls2, nullptr, 0, nullptr, 0, C, 1, 0, 0, 0, bw.b2));
     }
-    LEOD_TRY(prep_weight(dt, P + p.lstmw, nullptr, w.Wl, 2 * C, w.WlT, 4 * C, 4 * C, 2 * C, 0, 0, 0, st));
+    LEOD_TRY(add(P + p.lstmw, nullptr, w.Wl, 2 * C, w.WlT, 4 * C, 4 * C, 2 * C, 0, 0, 0, nullptr));
   }
+  LEOD_TRY(prep_batch_launch(dt, pb, blocks, st));
+  // the stem has no input gradient, so its transposed copy is unused: it holds the FP16 copy the implicit-GEMM forward reads
+  if (dt == LEOD_BF16) LEOD_TRY(stem_weight_to_f16(h->w[0].Wconv, h->w[0].WconvT, (int64_t)h->d[0].C * h->d[0].Kp, st));
   return 0;
 }
 
@@ -916,6 +929,8 @@ extern "C" int leod_backbone_grads_finalize(leod_backbone_t *h, void *stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const float *P = h->params;
   float *G = h->grads;
+  LsBatch lsb;
+  int ls_blocks = 0;
   for (int s = 0; s < 4; ++s) {
     const StageD &d = h->d[s];
     const StageP &p = h->p[s];
@@ -932,11 +947,10 @@ extern "C" int leod_backbone_grads_finalize(leod_backbone_t *h, void *stream) {
     for (int b = 0; b < 2; ++b) {
       const BlockP &q = p.blk[b];
       const BlockW &bw = w.blk[b];
-      LEOD_TRY(layerscale_grad_finalize(bw.Gproj, bw.sproj, P + q.projw, P + q.projb, P + q.ls1, G + q.projw, G + q.projb,
-                                        G + q.ls1, C, C, st));
-      LEOD_TRY(layerscale_grad_finalize(bw.G2, bw.s2, P + q.fc2w, P + q.fc2b, P + q.ls2, G + q.fc2w, G + q.fc2b, G + q.ls2, C,
-                                        R * C, st));
+      LEOD_TRY(ls_batch_add(lsb, ls_blocks, bw.Gproj, bw.sproj, P + q.projw, P + q.projb, P + q.ls1, G + q.projw, G + q.projb, G + q.ls1, C, C));
+      LEOD_TRY(ls_batch_add(lsb, ls_blocks, bw.G2, bw.s2, P + q.fc2w, P + q.fc2b, P + q.ls2, G + q.fc2w, G + q.fc2b, G + q.ls2, C, R * C));
     }
   }
+  LEOD_TRY(ls_batch_launch(lsb, ls_blocks, st));     // the 16 LayerScale gradients of the backbone in one launch
   return 0;
 }

@@ -183,6 +183,28 @@ int col2im_nhwc(int dtype, const void *dcol, int ldcol, const void *dres, void *
                 int stride, int pad, cudaStream_t st);
 // weight preparation: dst[n, k] = scale[n] * src(n, k)  (+ transposed copy dstT[k, n])
 //   perm: 0 = src is [N, K] row-major;  1 = src is conv weight [N, Cin, kh, kw], k index = (ky*kw + kx)*Cin + cin
+// batched weight preparation / LayerScale gradient finalisation (kernels_elem.cu): items are passed in the kernel parameters
+constexpr int PREP_BATCH_MAX = 30, LS_BATCH_MAX = 32;
+struct PrepItem {
+  const float *src, *scale;
+  void *dst, *dstT;
+  float *bias_out;     // != NULL: a scaled bias (out = src * scale, N elements) instead of a weight matrix
+  int ldd, lddT, N, K, perm, Cin, ksz, first_block;
+};
+struct PrepBatch { PrepItem it[PREP_BATCH_MAX]; int n = 0; };
+struct LsItem {
+  float *G, *s;
+  const float *W, *b, *gamma;
+  float *dW, *db, *dgamma;
+  int N, K, first_block, pad_;
+};
+struct LsBatch { LsItem it[LS_BATCH_MAX]; int n = 0; };
+int prep_batch_add(PrepBatch &pb, int &blocks, const float *src, const float *scale, void *dst, int ldd, void *dstT, int lddT, int N, int K,
+                   int perm, int Cin, int ksz, float *bias_out);
+int prep_batch_launch(int dtype, const PrepBatch &pb, int blocks, cudaStream_t st);
+int ls_batch_add(LsBatch &lb, int &blocks, float *G, float *s, const float *W, const float *b, const float *gamma, float *dW, float *db,
+                 float *dgamma, int N, int K);
+int ls_batch_launch(const LsBatch &lb, int blocks, cudaStream_t st);
 int prep_weight(int dtype, const float *src, const float *scale, void *dst, int ldd, void *dstT, int lddT, int N, int K, int perm,
                 int Cin, int ksz, cudaStream_t st);
 int prep_scaled_bias(const float *b, const float *scale, float *out, int N, cudaStream_t st);

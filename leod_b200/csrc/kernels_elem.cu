@@ -544,6 +544,62 @@ __global__ void ls_finalize_kernel(float *__restrict__ G, float *__restrict__ s,
   }
 }
 
+// ---- batched variants: one launch for many small tensors (the per-tensor launches above cost more in launch gaps than in work:
+// 57 weight/bias tensors are prepared after every optimizer step, 16 LayerScale gradients are finalised after every backward)
+template <typename T>
+__global__ void prep_batch_kernel(const __grid_constant__ PrepBatch pb) {
+  pdl_prologue();
+  int it = 0;
+  while (it + 1 < pb.n && (int)blockIdx.x >= pb.it[it + 1].first_block) ++it;
+  const PrepItem &d = pb.it[it];
+  const int64_t idx = (int64_t)(blockIdx.x - d.first_block) * blockDim.x + threadIdx.x;
+  if (d.bias_out) {   // scaled bias: out = b * scale
+    if (idx < d.N) d.bias_out[idx] = d.src[idx] * d.scale[idx];
+    return;
+  }
+  if (idx >= (int64_t)d.N * d.K) return;
+  const int n = (int)(idx / d.K), k = (int)(idx % d.K);
+  size_t si = idx;
+  bool zero = false;
+  if (d.perm == 1) {
+    const int cin = k % d.Cin, kx = (k / d.Cin) % d.ksz, ky = k / (d.Cin * d.ksz);
+    si = (((size_t)n * d.Cin + cin) * d.ksz + ky) * d.ksz + kx;
+  } else if (d.perm == 2) {
+    const int slot = k & 7, r = k >> 3;
+    zero = slot == 0 || slot > d.ksz;
+    si = (size_t)n * d.Cin * d.ksz * d.ksz + (size_t)r * d.ksz + (slot - 1);
+  }
+  float v = zero ? 0.f : d.src[si];
+  if (d.scale) v *= d.scale[n];
+  const T t = from_f<T>(v);
+  if (d.dst) reinterpret_cast<T *>(d.dst)[(size_t)n * d.ldd + k] = t;
+  if (d.dstT) reinterpret_cast<T *>(d.dstT)[(size_t)k * d.lddT + n] = t;
+}
+
+__global__ void ls_finalize_batch_kernel(const __grid_constant__ LsBatch lb) {
+  pdl_prologue();
+  int it = 0;
+  while (it + 1 < lb.n && (int)blockIdx.x >= lb.it[it + 1].first_block) ++it;
+  const LsItem &d = lb.it[it];
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x - d.first_block) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= d.N) return;
+  const float gm = d.gamma[n];
+  float dot = 0.f;
+  for (int k = lane; k < d.K; k += 32) {
+    const float g = d.G[(size_t)n * d.K + k];
+    dot += d.W[(size_t)n * d.K + k] * g;
+    d.dW[(size_t)n * d.K + k] += gm * g;
+    d.G[(size_t)n * d.K + k] = 0.f;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    d.dgamma[n] += dot + d.b[n] * d.s[n];
+    d.db[n] += gm * d.s[n];
+    d.s[n] = 0.f;
+  }
+}
+
 inline int blocks_for(int64_t n, int bs) { return (int)((n + bs - 1) / bs); }
 
 // SM-side copy / clear for small buffers on the compute stream.  cudaMemcpyAsync / cudaMemsetAsync would go to a copy
@@ -709,6 +765,38 @@ int prep_weight(int dtype, const float *src, const float *scale, void *dst, int 
 
 int prep_scaled_bias(const float *b, const float *scale, float *out, int N, cudaStream_t st) {
   LEOD_LAUNCH((scaled_bias_kernel), blocks_for(N, 128), 128, 0, st, b, scale, out, N);
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+
+int prep_batch_add(PrepBatch &pb, int &blocks, const float *src, const float *scale, void *dst, int ldd, void *dstT, int lddT, int N, int K,
+                   int perm, int Cin, int ksz, float *bias_out) {
+  if (pb.n >= PREP_BATCH_MAX) return -1;
+  PrepItem &d = pb.it[pb.n++];
+  d.src = src; d.scale = scale; d.dst = dst; d.dstT = dstT; d.bias_out = bias_out;
+  d.ldd = ldd; d.lddT = lddT; d.N = N; d.K = K; d.perm = perm; d.Cin = Cin; d.ksz = ksz;
+  d.first_block = blocks;
+  blocks += (int)(((int64_t)N * (bias_out ? 1 : K) + 255) / 256);
+  return 0;
+}
+int prep_batch_launch(int dtype, const PrepBatch &pb, int blocks, cudaStream_t st) {
+  if (pb.n == 0) return 0;
+  DISPATCH_T(dtype, (LEOD_LAUNCH((prep_batch_kernel<T>), blocks, 256, 0, st, pb)));
+  LEOD_LAUNCH_CHECK();
+  return 0;
+}
+int ls_batch_add(LsBatch &lb, int &blocks, float *G, float *s, const float *W, const float *b, const float *gamma, float *dW, float *db,
+                 float *dgamma, int N, int K) {
+  if (lb.n >= LS_BATCH_MAX) return -1;
+  LsItem &d = lb.it[lb.n++];
+  d.G = G; d.s = s; d.W = W; d.b = b; d.gamma = gamma; d.dW = dW; d.db = db; d.dgamma = dgamma; d.N = N; d.K = K;
+  d.first_block = blocks;
+  blocks += ceil_div(N, 8);
+  return 0;
+}
+int ls_batch_launch(const LsBatch &lb, int blocks, cudaStream_t st) {
+  if (lb.n == 0) return 0;
+  LEOD_LAUNCH((ls_finalize_batch_kernel), blocks, 256, 0, st, lb);
   LEOD_LAUNCH_CHECK();
   return 0;
 }

@@ -125,21 +125,6 @@ __device__ __forceinline__ void nt_epilogue_chunk(const GemmNT &g, const uint32_
   }
 }
 
-// erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below bf16 resolution) on the MUFU rcp / ex2 units: about a
-// third of the instructions of erff().  e = exp(-x^2/2) is shared between GELU and its derivative.
-__device__ __forceinline__ void gelu_parts_fast(float x, float &cdf, float &e) {
-  const float ax = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * ax * ax));
-  const float h = 0.5f * p * e;               // 0.5 * (1 - erf(|x|/sqrt2))
-  cdf = x >= 0.f ? 1.0f - h : h;
-}
 // Packed fp32 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two lanes per instruction).  The GELU epilogue is bound by instruction
 // issue, not by HBM (profiles/r02_ncu_full_gemm_nt_gelu_stage1_details.txt: 30 instructions per element, IPC 2.1 of 4), so the
 // polynomial part is evaluated on pairs of columns.
@@ -162,8 +147,8 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
   return d;
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
-// GELU(x) = x Phi(x) and GELU'(x) = Phi(x) + x phi(x) of two columns.  Same erf approximation as gelu_parts_fast (Abramowitz-Stegun
-// 7.1.26 on MUFU rcp / ex2), rearranged so that every multiply-add is packed:  E = phi(x) = 2^(-x^2 log2(e)/2 + log2(1/sqrt(2 pi))),
+// GELU(x) = x Phi(x) and GELU'(x) = Phi(x) + x phi(x) of two columns.  erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below
+// bf16 resolution) on the MUFU rcp / ex2 units, rearranged so that every multiply-add is packed:  E = phi(x) = 2^(-x^2 log2(e)/2 + log2(1/sqrt(2 pi))),
 // h = 0.5 erfc(|x|/sqrt2) = (poly(t) t) E with the 0.5 sqrt(2 pi) folded into the coefficients,  Phi = 0.5 + sign(x) (0.5 - h).
 __device__ __forceinline__ void gelu_pair(float2 x, float2 &H, float2 &G) {
   const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
