@@ -35,6 +35,29 @@ def _h2d_async(t: torch.Tensor, device) -> torch.Tensor:
     return _lib.upload_small(t, device)
 
 
+class _SelectFrames(torch.autograd.Function):
+    """`features[ti, bi]` for the labelled (timestep, sequence) pairs, in the memory layout both neighbours use: the backbone's
+    feature maps are NCHW-shaped views of channels-last storage and the neck reads channels-last, but plain advanced indexing
+    returns an NCHW-contiguous copy (one transposing copy per pyramid level on the way in) and its backward builds an
+    NCHW-contiguous dense gradient (a second, window-sized transposing copy on the way back).  Here the gather and the scatter of
+    the gradient both happen on the channels-last tensors."""
+
+    @staticmethod
+    def forward(ctx, v, ti, bi):
+        vn = v.permute(0, 1, 3, 4, 2)                       # [L, B, h, w, C]; contiguous for the library's outputs
+        out = vn[ti, bi]                                    # [n, h, w, C]
+        ctx.save_for_backward(ti, bi)
+        ctx.full_shape = tuple(vn.shape)
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        ti, bi = ctx.saved_tensors
+        full = torch.zeros(ctx.full_shape, dtype=g.dtype, device=g.device)
+        full[ti, bi] = g.permute(0, 2, 3, 1)                # the (ti, bi) pairs are distinct: a plain scatter
+        return full.permute(0, 1, 4, 2, 3), None, None
+
+
 def get_subsample_label_idx(L: int, use_every: int = -1, remove_every: int = -1):
     """modules/utils/ssod.py:19-37."""
     assert use_every == -1 or remove_every == -1
@@ -119,7 +142,7 @@ class Module(_Base):
             labels_yolox = type(obj_labels[0]).get_labels_as_batched_tensor(obj_label_list=obj_labels, format_='yolox')
             labels_yolox = _h2d_async(labels_yolox.to(torch.float32), ev.device)
             feats_all, prev_states = self.mdl.backbone.forward_sequence(ev, prev_states)
-            sel = {k: v[ti, bi] for k, v in feats_all.items() if k in self.mdl.fpn.in_features}
+            sel = {k: _SelectFrames.apply(v, ti, bi) for k, v in feats_all.items() if k in self.mdl.fpn.in_features}
         else:
             selector = BackboneFeatureSelector()
             for tidx in range(L):
