@@ -1,6 +1,9 @@
-"""State / feature book-keeping of the step loops.  Mirror of modules/utils/detection.py:11-14
-(Mode), :27-58 (BackboneFeatureSelector), :95-157 (RNNStates) — same method names and semantics
-(states keyed by dataloader worker id, partial reset in place, detach between batches)."""
+"""State / feature book-keeping of the step loops.  This file is a TRANSCRIPTION of the host-side contract in the reference's
+modules/utils/detection.py:11-14 (Mode), :27-58 (BackboneFeatureSelector), :95-157 (RNNStates), :160-192 (SeqLens), :195-223
+(mixed_collate_fn): the callers keep their names and semantics (states keyed by dataloader worker id, partial reset in place,
+detach between batches), so the structure follows the reference statement for statement.  What is original here: the
+sync-free masked reset (no device->host round trip of boolean indexing) and the single small upload of a host mask
+(leod_upload_small) for all state tensors."""
 from enum import Enum, auto
 from typing import Dict, List, Optional, Union
 
