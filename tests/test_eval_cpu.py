@@ -70,3 +70,23 @@ def test_filter_drops_frames_and_boxes():
     frames, ann, res = oc.to_coco_records([g_early, g_small, g_ok], [dict(d, t=np.full(1, 400000)), d, d], 'gen1', False)
     assert frames.tolist() == [2] and len(ann) == 1 and len(res) == 1
     assert oc.evaluate_frames([g_early], [dict(d, t=np.full(1, 400000))], 'gen1', False) is None
+
+
+def test_per_class_evaluation_and_host_summarize():
+    """evaluator.py:95-105: the per-class numbers come from buffers filtered to that class BEFORE everything else (frames whose only
+    ground truth is of another class stop being images); the host mirror's summarize equals the oracle's on the same arrays."""
+    from leod_b200.utils.evaluation.prophesee import evaluator as ev
+    g0 = _frame([[10, 10, 40, 40]], [0])                      # frame with a class-0 box only
+    g1 = _frame([[50, 60, 45, 35]], [1], t=2 * 10 ** 6)       # frame with a class-1 box only
+    d0 = _frame([[10, 10, 40, 40], [100, 100, 40, 40]], [0, 1], [0.9, 0.8])            # class-1 false positive in frame 0
+    d1 = _frame([[50, 60, 45, 35]], [1], [0.7], t=2 * 10 ** 6)
+    all_stats, p_all, r_all = oc.evaluate_frames([g0, g1], [d0, d1], 'gen1', False)
+    c1_stats, p1, r1 = oc.evaluate_frames([g0, g1], [d0, d1], 'gen1', False, only_class=1)
+    # overall: class 1 sees its false positive (score 0.8) ranked above the true positive (0.7): AP50 of class 1 = 0.5
+    assert abs(p_all[0, :, 1, 0, 2].mean() - 0.5) < 1e-12 and abs(p_all[0, :, 0, 0, 2].mean() - 1.0) < 1e-12
+    # per class: frame 0 has no class-1 ground truth, so it is no image and its false positive is never seen
+    assert abs(c1_stats[1] - 1.0) < 1e-12 and (p1[:, :, 0] == -1).all()
+    np.testing.assert_array_equal(ev.summarize(p_all, r_all), all_stats)
+    np.testing.assert_array_equal(ev.IOU_THRS, oc.IOU_THRS)
+    np.testing.assert_array_equal(ev.REC_THRS, oc.REC_THRS)
+    assert ev.filter_thresholds('gen4', True) == oc.filter_thresholds('gen4', True) == (500000, 30, 10)
