@@ -35,6 +35,7 @@ struct NtArgs {
   int staged;     // epilogue writes through shared memory (N multiple of 16: every chunk is full)
   int kpb;        // implicit-GEMM taps (g.taps.n > 1): k-blocks per tap
   int nbuf;       // accumulator buffers in TMEM (2..4): narrow tiles let the MMA warp run further ahead of the epilogue
+  int tma_store;  // full 64-column groups of the staged epilogue leave through cp.async.bulk.tensor stores (mapC / mapAux)
   int bias_smem;  // the bias vector (N floats) is staged in shared memory once per CTA (staged epilogue, N <= 2048)
 };
 
@@ -261,6 +262,14 @@ __device__ __forceinline__ void nt_flush_stage(const uint8_t *stage, bf16 *dst, 
   }
 }
 
+// TMA store of a staged [32 rows x 64 columns] bf16 block (SWIZZLE_128B layout = the epilogue's staging layout) and its bookkeeping
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Persistent: every CTA walks the tile list with stride gridDim.x (n-tile fastest, so CTAs running side by side share
 // an A tile through L2).  The TMA ring runs ahead across tile boundaries, the accumulator is double-buffered in TMEM
 // so the MMAs of tile j+1 overlap the epilogue of tile j, and eight epilogue warps (two per TMEM lane quarter, each
@@ -269,7 +278,9 @@ template <int EPI>   // EPI_* : staged epilogue specialised for that mode;  -1 :
 __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                     const __grid_constant__ CUtensorMap mapA2,
                                                                     const __grid_constant__ CUtensorMap mapB,
-                                                                    const __grid_constant__ CUtensorMap mapB2, const NtArgs a) {
+                                                                    const __grid_constant__ CUtensorMap mapB2,
+                                                                    const __grid_constant__ CUtensorMap mapC,
+                                                                    const __grid_constant__ CUtensorMap mapAux, const NtArgs a) {
   pdl_launch_dependents();   // the next kernel of the stream may start its own prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -278,8 +289,9 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
   uint64_t *bars = (uint64_t *)(smem + (size_t)a.stages * stage_bytes);
   uint64_t *full_bar = bars, *empty_bar = bars + a.stages, *tmem_full = bars + 2 * a.stages, *tmem_empty = tmem_full + 4;
   uint32_t *tmem_slot = (uint32_t *)(tmem_empty + 4);
-  // per epilogue warp: two 4 KB staging blocks (32 rows x 64 columns bf16), 128-byte aligned
-  uint8_t *stage_base = (uint8_t *)(((uintptr_t)(tmem_slot + 4) + 127) & ~(uintptr_t)127);
+  // per epilogue warp: 4 KB staging blocks (32 rows x 64 columns bf16, 128-byte rows, 16-byte chunk c of row r at chunk c ^ (r & 7)):
+  // 1024-byte aligned, so a block is exactly a SWIZZLE_128B TMA box {64, 32}
+  uint8_t *stage_base = (uint8_t *)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = a.tiles_m * a.tiles_n;
@@ -375,6 +387,7 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
       s_bias = sb;
     }
     int j = 0;
+    bool store_pending = false;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const int m0 = (tile / a.tiles_n) * TILE_M, n0 = (tile % a.tiles_n) * a.BN;
       const int buf = j % a.nbuf;
@@ -420,6 +433,11 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
             nt_epilogue_compute<EPI>(g, rbuf[hh & RB], m, n0 + cc * 16, row_ok, o, t, s_bias, pre[hh]);
             if (!RB && cc + 1 < c_end) tmem_ld16_async(trow + (uint32_t)((cc + 1) * 16), rbuf[0]);
             const int slot = (cc - gs) * 2, sw = lane & 7;
+            if (store_pending && cc == gs) {   // the previous group's tensor store must have read the staging block
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+              store_pending = false;
+            }
             *reinterpret_cast<uint4 *>(stC + lane * 128 + (((slot) ^ sw) << 4)) = o[0];
             *reinterpret_cast<uint4 *>(stC + lane * 128 + (((slot + 1) ^ sw) << 4)) = o[1];
             if (EPI == EPI_GELU) {
@@ -427,11 +445,24 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
               *reinterpret_cast<uint4 *>(stT + lane * 128 + (((slot + 1) ^ sw) << 4)) = t[1];
             }
             if (cc - gs == 3 || cc == c_end - 1) {
-              __syncwarp();
               const int gc = cc - gs + 1;
-              nt_flush_stage(stC, (bf16 *)g.C, g.ldc, m_base, g.M, n0 + gs * 16, gc, lane);
-              if (EPI == EPI_GELU) nt_flush_stage(stT, (bf16 *)g.aux, g.ldaux, m_base, g.M, n0 + gs * 16, gc, lane);
-              __syncwarp();
+              if (a.tma_store && gc == 4) {
+                // a full 64-column group: the staged block leaves as ONE asynchronous tensor store per output (rows beyond M are
+                // clipped by the tensor map) instead of 8 x (ld.shared + st.global) per lane on the warps that pace the kernel
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                  tma_store_2d(&mapC, smem_u32(stC), n0 + gs * 16, m_base);
+                  if (EPI == EPI_GELU) tma_store_2d(&mapAux, smem_u32(stT), n0 + gs * 16, m_base);
+                  tma_store_commit();
+                }
+                store_pending = true;
+              } else {
+                __syncwarp();
+                nt_flush_stage(stC, (bf16 *)g.C, g.ldc, m_base, g.M, n0 + gs * 16, gc, lane);
+                if (EPI == EPI_GELU) nt_flush_stage(stT, (bf16 *)g.aux, g.ldaux, m_base, g.M, n0 + gs * 16, gc, lane);
+                __syncwarp();
+              }
               gs = cc + 1;
             }
           }
@@ -455,6 +486,7 @@ __global__ void __launch_bounds__(64 + 32 * NtEpiWarps<EPI>::value, 1) gemm_nt_t
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
     }
+    if (a.tma_store && lane == 0) tma_store_wait_all();   // outstanding tensor stores complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
@@ -1365,7 +1397,7 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   const bool gelu_like = a.staged && g.epi == EPI_GELU;
   const int epi_warps = gelu_like ? NtEpiWarps<EPI_GELU>::value : NtEpiWarps<EPI_NONE>::value;
   a.bias_smem = (a.staged && g.bias && g.N <= 2048) ? 1 : 0;
-  const int epi_bytes = epi_warps * ((a.staged && g.epi == EPI_GELU) ? 8192 : 4096) + 256 + (a.bias_smem ? (int)round_up(g.N * 4, 16) : 0);
+  const int epi_bytes = epi_warps * ((a.staged && g.epi == EPI_GELU) ? 8192 : 4096) + 1024 /*staging alignment*/ + (a.bias_smem ? (int)round_up(g.N * 4, 16) : 0);
   a.stages = std::min(std::min(4, (int)((224 * 1024 - epi_bytes - 2048) / stage_bytes)), std::max(total_kb, 1));
   CUtensorMap mA, mA2, mB, mB2;
   LEOD_TRY(make_map(&mA, g.A, tapped ? g.taps.cin : K1, g.M, g.lda, TILE_K, TILE_M));
@@ -1376,6 +1408,15 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   } else {
     mA2 = mA;
     mB2 = mB;
+  }
+  // tensor stores of the staged epilogue: C (and the GELU' side output) as [M, N] bf16 matrices, box = one staging block
+  CUtensorMap mC = mA, mAux = mA;
+  a.tma_store = 0;
+  if (a.staged && g.N >= 64 && (((uintptr_t)g.C) & 15) == 0 && g.ldc % 8 == 0 &&
+      (g.epi != EPI_GELU || (g.aux && (((uintptr_t)g.aux) & 15) == 0 && g.ldaux % 8 == 0))) {
+    LEOD_TRY(make_map(&mC, g.C, g.N, g.M, g.ldc, 64, 32));
+    if (g.epi == EPI_GELU) LEOD_TRY(make_map(&mAux, g.aux, g.N, g.M, g.ldaux, 64, 32));
+    a.tma_store = 1;
   }
   const size_t smem = (size_t)a.stages * stage_bytes + 1024 /*align*/ + (2 * a.stages + 8) * 8 + 16 + epi_bytes;
   static bool attr_set = false;
@@ -1393,15 +1434,15 @@ int gemm_nt_tc(const GemmNT &g, cudaStream_t st) {
   const int grid = ceil_div(tiles, waves);
   const int threads = 64 + 32 * epi_warps;
   if (!a.staged) {
-    LEOD_LAUNCH((gemm_nt_tc_kernel<-1>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<-1>), grid, threads, smem, st, mA, mA2, mB, mB2, mC, mAux, a);
   } else if (g.epi == EPI_GELU) {
-    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_GELU>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_GELU>), grid, threads, smem, st, mA, mA2, mB, mB2, mC, mAux, a);
   } else if (g.epi == EPI_RESID) {
-    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_RESID>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_RESID>), grid, threads, smem, st, mA, mA2, mB, mB2, mC, mAux, a);
   } else if (g.epi == EPI_GELU_BWD) {
-    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_GELU_BWD>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_GELU_BWD>), grid, threads, smem, st, mA, mA2, mB, mB2, mC, mAux, a);
   } else {
-    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_NONE>), grid, threads, smem, st, mA, mA2, mB, mB2, a);
+    LEOD_LAUNCH((gemm_nt_tc_kernel<EPI_NONE>), grid, threads, smem, st, mA, mA2, mB, mB2, mC, mAux, a);
   }
   LEOD_LAUNCH_CHECK();
   return 0;
