@@ -14,8 +14,8 @@ Restates, for the way LEOD calls it (one entry per labelled frame in the evaluat
                             precision envelope, precision sampled at 101 recall thresholds (searchsorted left)
     summarize             — AP, AP50, AP75, AP_S, AP_M, AP_L (mean of the precision entries > -1), AR@1/10/100, AR_S/M/L
 Parity status of THIS file: the Prophesee half is pinned by fixtures made from the reference's own functions (tests/golden/
-eval_cases.npz); the COCOeval half is PARITY UNPINNED — pycocotools cannot be run here; it is checked against analytic cases only
-(tests/test_eval_cpu.py).
+eval_cases.npz); the COCOeval half is PARITY UNPINNED — pycocotools cannot be run here; it is checked against analytic cases and
+against a second, differently structured AP computation on seeded buffers (tests/test_eval_cpu.py).
 TEST INFRASTRUCTURE — see oracle/__init__.py.
 """
 import numpy as np

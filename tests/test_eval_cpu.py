@@ -90,3 +90,60 @@ def test_per_class_evaluation_and_host_summarize():
     np.testing.assert_array_equal(ev.IOU_THRS, oc.IOU_THRS)
     np.testing.assert_array_equal(ev.REC_THRS, oc.REC_THRS)
     assert ev.filter_thresholds('gen4', True) == oc.filter_thresholds('gen4', True) == (500000, 30, 10)
+
+
+def _ap_independent(gts, dts, k, thr):
+    """A second, differently structured computation of one COCO number (class k, one IoU threshold, area 'all', maxDets 100):
+    vectorised IoU, per-image greedy matching by masked argmax, precision envelope by a reversed running maximum."""
+    scores, tps, n_gt = [], [], 0
+    skip, diag, side = oc.filter_thresholds('gen1', False)
+    for g, d in zip(gts, dts):
+        gk = (g['t'] > skip) & (g['xywh'][:, 2] ** 2 + g['xywh'][:, 3] ** 2 >= diag ** 2) & (g['xywh'][:, 2] >= side) & (g['xywh'][:, 3] >= side)
+        dk = (d['t'] > skip) & (d['xywh'][:, 2] ** 2 + d['xywh'][:, 3] ** 2 >= diag ** 2) & (d['xywh'][:, 2] >= side) & (d['xywh'][:, 3] >= side)
+        if not gk.any():
+            continue
+        gb = g['xywh'][gk & (g['cls'] == k)].astype(np.float64)
+        db = d['xywh'][dk & (d['cls'] == k)].astype(np.float64)
+        ds = d['score'][dk & (d['cls'] == k)].astype(np.float64)
+        order = np.argsort(-ds, kind='stable')[:100]
+        db, ds = db[order], ds[order]
+        n_gt += len(gb)
+        if len(gb) and len(db):
+            x1 = np.maximum(db[:, None, 0], gb[None, :, 0]); y1 = np.maximum(db[:, None, 1], gb[None, :, 1])
+            x2 = np.minimum(db[:, None, 0] + db[:, None, 2], gb[None, :, 0] + gb[None, :, 2])
+            y2 = np.minimum(db[:, None, 1] + db[:, None, 3], gb[None, :, 1] + gb[None, :, 3])
+            w, h = x2 - x1, y2 - y1
+            inter = np.where((w > 0) & (h > 0), w * h, 0.0)
+            iou = inter / (db[:, None, 2] * db[:, None, 3] + gb[None, :, 2] * gb[None, :, 3] - inter)
+        else:
+            iou = np.zeros((len(db), len(gb)))
+        free = np.ones(len(gb), bool)
+        for i in range(len(db)):
+            cand = np.where(free & (iou[i] >= min(thr, 1 - 1e-10)))[0] if len(gb) else []
+            hit = len(cand) > 0
+            if hit:
+                best = cand[np.flatnonzero(iou[i, cand] == iou[i, cand].max())[-1]]      # equal IoU: the later ground-truth box wins
+                free[best] = False
+            scores.append(ds[i]); tps.append(hit)
+    if n_gt == 0:
+        return -1.0
+    scores, tps = np.array(scores), np.array(tps, bool)
+    o = np.argsort(-scores, kind='stable')
+    tp = np.cumsum(tps[o]).astype(float); fp = np.cumsum(~tps[o]).astype(float)
+    rc, pr = tp / n_gt, tp / (tp + fp + np.spacing(1))
+    env = np.maximum.accumulate(pr[::-1])[::-1] if len(pr) else pr
+    idx = np.searchsorted(rc, oc.REC_THRS, side='left')
+    q = np.array([env[i] if i < len(env) else 0.0 for i in idx])
+    return q.mean()
+
+
+def test_oracle_agrees_with_independent_ap_computation():
+    for seed in (31, 32, 33):
+        gts, dts = eval_inputs('gen1', False, 40, seed, max_gt=6, fp_rate=4.0)
+        _, precision, _ = oc.evaluate_frames(gts, dts, 'gen1', False)
+        for k in (0, 1):
+            for ti, thr in ((0, 0.5), (5, oc.IOU_THRS[5]), (9, oc.IOU_THRS[9])):
+                want = _ap_independent(gts, dts, k, thr)
+                got = precision[ti, :, k, 0, 2]
+                got = -1.0 if (got == -1).all() else got.mean()
+                assert abs(got - want) < 1e-12, (seed, k, thr, got, want)
